@@ -1,0 +1,100 @@
+"""ctypes binding of ``include/b200icp.h`` (the drop-in C ABI).
+
+There is NO fallback: if ``lib/libb200icp.so`` is missing or does not export every
+symbol the header declares, importing this module's :func:`lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+
+OK = 0
+F32, F64 = 0, 1
+PAIR_ROWWISE, PAIR_EXPLICIT, PAIR_TRIANGLE = 0, 1, 2
+
+STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "CUDA", 4: "NO_DEVICE"}
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("src_points", C.c_void_p), ("tgt_points", C.c_void_p),
+        ("src_len", C.c_void_p), ("tgt_len", C.c_void_p),
+        ("src_pitch", C.c_int32), ("tgt_pitch", C.c_int32),
+        ("dtype", C.c_int32), ("pairing", C.c_int32),
+        ("src_row", C.c_void_p), ("tgt_row", C.c_void_p),
+        ("first_pair", C.c_int64), ("n_rows", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("max_iterations", C.c_int32), ("reserved", C.c_int32),
+        ("tolerance", C.c_double), ("max_corr_dist", C.c_double),
+        ("init_pose", C.c_void_p),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [
+        ("pose_total", C.c_void_p), ("pose_last", C.c_void_p), ("error", C.c_void_p),
+        ("rmse", C.c_void_p), ("inliers", C.c_void_p), ("iterations", C.c_void_p),
+        ("indices", C.c_void_p), ("src_final", C.c_void_p), ("index_history", C.c_void_p),
+    ]
+
+
+# symbol -> (restype, argtypes); must list EVERY function include/b200icp.h declares
+SYMBOLS = {
+    "b200icp_version": (C.c_int, []),
+    "b200icp_last_error": (C.c_char_p, []),
+    "b200icp_max_src_pitch": (C.c_int, []),
+    "b200icp_max_tgt_pitch": (C.c_int, []),
+    "b200icp_nn_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200icp_align_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.POINTER(Options),
+                                      C.POINTER(Outputs), C.c_void_p]),
+    "b200icp_polar_to_cartesian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "b200icp_ffma_probe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_void_p]),
+}
+
+_lib = None
+
+
+class B200IcpError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib():
+    """Load (once) and return the CUDA library.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise B200IcpError(
+            f"{path} is missing: the CUDA library has not been built and there is no CPU "
+            "fallback.  Run `python -c \"import __graft_entry__ as g; g.build()\"` in the repo root.")
+    handle = C.CDLL(path)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as e:
+            raise B200IcpError(f"{path} does not export {name}; rebuild it") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != OK:
+        msg = lib().b200icp_last_error().decode("utf-8", "replace")
+        raise B200IcpError(f"{what} failed: {STATUS_NAMES.get(status, status)}: {msg}")

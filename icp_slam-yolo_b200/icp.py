@@ -1,0 +1,126 @@
+"""Drop-in mirror of the reference's ICP call surface, executed on the B200.
+
+Same names, argument meaning and return shapes as
+``labels_segmentation/icp.py`` (``icp`` :28-53, ``best_fit_transform`` :5-26) and the
+Open3D-shaped wrapper ``gicp`` (duc/ICP_LIDAR/gicp_lidar.py:12-36), with NumPy arrays in
+and out like the reference.  All arithmetic runs in the CUDA library through the C ABI;
+nothing here computes on the host and nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .registration import ScanTable, align_pairs, nn_search
+
+
+@dataclass
+class IcpOutput:
+    R: np.ndarray            # (2,2) cumulative rotation,  src = R A + t
+    t: np.ndarray            # (2,)
+    error: float             # mean NN distance of the last search (lagged, icp.py:48)
+    iterations: int
+    R_last: np.ndarray       # last increment (what the reference's icp() returns)
+    t_last: np.ndarray
+    rmse: float
+    fitness: float
+    indices: np.ndarray      # (N,) correspondences of the last search
+    src: np.ndarray          # (N,2) transformed source
+
+
+def _as_points(a, name: str) -> np.ndarray:
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2 or a.shape[1] < 2:
+        raise ValueError(f"{name} must be an (N, 2) array, got shape {a.shape}")
+    if a.shape[0] == 0:
+        # the reference fails inside SciPy on empty input
+        raise ValueError(f"{name} is empty")
+    return np.ascontiguousarray(a[:, :2])
+
+
+def _pose6(init_pose) -> Optional[torch.Tensor]:
+    if init_pose is None:
+        return None
+    if isinstance(init_pose, (tuple, list)) and len(init_pose) == 2:
+        R0, t0 = np.asarray(init_pose[0], dtype=np.float64), np.asarray(init_pose[1], dtype=np.float64)
+    else:
+        T = np.asarray(init_pose, dtype=np.float64)
+        if T.shape == (4, 4):            # Open3D trans_init (gicp_lidar.py:12)
+            R0, t0 = T[:2, :2], T[:2, 3]
+        elif T.shape == (3, 3):
+            R0, t0 = T[:2, :2], T[:2, 2]
+        else:
+            raise ValueError("init_pose must be (R, t), a 3x3 or a 4x4 homogeneous matrix")
+    p = np.concatenate([R0.reshape(4), t0.reshape(2)])[None, :]
+    return torch.from_numpy(np.ascontiguousarray(p)).cuda()
+
+
+def icp_full(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_pose=None,
+             max_corr_dist: Optional[float] = None) -> IcpOutput:
+    """One alignment with every output of the new call surface."""
+    A = _as_points(A, "A")
+    B = _as_points(B, "B")
+    src = ScanTable(torch.from_numpy(A[None]).cuda(), None)
+    tgt = ScanTable(torch.from_numpy(B[None]).cuda(), None)
+    res = align_pairs(src, tgt, n_pairs=1, max_iterations=max_iterations, tolerance=tolerance,
+                      init_pose=_pose6(init_pose), max_corr_dist=max_corr_dist,
+                      want_indices=True, want_src=True)
+    pt = res.pose_total[0].cpu().numpy()
+    pl = res.pose_last[0].cpu().numpy()
+    inl = int(res.inliers[0].item())
+    return IcpOutput(
+        R=pt[:4].reshape(2, 2).copy(), t=pt[4:6].copy(),
+        error=float(res.error[0].item()), iterations=int(res.iterations[0].item()),
+        R_last=pl[:4].reshape(2, 2).copy(), t_last=pl[4:6].copy(),
+        rmse=float(res.rmse[0].item()), fitness=inl / float(len(A)),
+        indices=res.indices[0].cpu().numpy().astype(np.intp),
+        src=res.src_final[0].cpu().numpy(),
+    )
+
+
+def icp(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_pose=None,
+        max_corr_dist: Optional[float] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """``icp(A, B, max_iterations=20, tolerance=1e-5) -> (src, R, t)``.
+
+    Positional-compatible with labels_segmentation/icp.py:28.  Like the reference, the
+    returned ``R, t`` are the LAST incremental update (icp.py:42,53), not the cumulative
+    pose; use :func:`icp_full` for the cumulative pose, error and iteration count.
+    """
+    o = icp_full(A, B, max_iterations, tolerance, init_pose=init_pose, max_corr_dist=max_corr_dist)
+    return o.src, o.R_last, o.t_last
+
+
+def nearest_neighbors(src, tgt) -> Tuple[np.ndarray, np.ndarray]:
+    """``distances, indices = KDTree(tgt).query(src)`` (icp.py:37-38) on the device."""
+    A = _as_points(src, "src")
+    B = _as_points(tgt, "tgt")
+    s = ScanTable(torch.from_numpy(A[None]).cuda(), None)
+    t = ScanTable(torch.from_numpy(B[None]).cuda(), None)
+    idx, d2 = nn_search(s, t, n_pairs=1)
+    return np.sqrt(d2[0].cpu().numpy()), idx[0].cpu().numpy().astype(np.intp)
+
+
+def registration_p2p(points1, points2, threshold: float = 200.0, trans_init=None,
+                     max_iteration: int = 50, tolerance: float = 1e-5):
+    """Open3D-shaped point-to-point adapter: ``(rmse, T4x4)``.
+
+    Mirrors the call shape of ``gicp(points1, points2, threshold, voxel, trans_init)``
+    (duc/ICP_LIDAR/gicp_lidar.py:12-36; caller duc/ICP_LIDAR/mainn.py:311) and of
+    ``icp(...)`` in duc/code python/b.py:219-236, including the ``< 10`` points guard
+    (gicp_lidar.py:13-15).  Gate / rmse semantics are parity-unpinned (Open3D is not
+    vendored by the reference) and are defined by oracle.icp_oracle.icp_extended.
+    """
+    p1 = np.asarray(points1, dtype=np.float64)
+    p2 = np.asarray(points2, dtype=np.float64)
+    if len(p1) < 10 or len(p2) < 10:
+        return float("inf"), np.eye(4)
+    o = icp_full(p1, p2, max_iteration, tolerance,
+                 init_pose=None if trans_init is None else np.asarray(trans_init),
+                 max_corr_dist=threshold)
+    T = np.eye(4)
+    T[:2, :2] = o.R
+    T[:2, 3] = o.t
+    return o.rmse, T

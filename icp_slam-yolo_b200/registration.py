@@ -1,0 +1,279 @@
+"""Batched device-side registration: PyTorch tensors in and out, CUDA through the C ABI.
+
+This is the host-side mirror of the reference's registration boundary
+(labels_segmentation/icp.py:28-53) for *batches* of scan pairs.  Tensors only carry
+device memory and the stream; every computation happens in ``libb200icp.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_DTYPES = {torch.float32: _cabi.F32, torch.float64: _cabi.F64}
+_PAIRINGS = {"rowwise": _cabi.PAIR_ROWWISE, "explicit": _cabi.PAIR_EXPLICIT,
+             "triangle": _cabi.PAIR_TRIANGLE}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _cabi.B200IcpError(f"{name} must be a CUDA tensor: this path has no CPU fallback")
+    if not t.is_contiguous():
+        raise _cabi.B200IcpError(f"{name} must be contiguous")
+
+
+@dataclass
+class ScanTable:
+    """Ragged scans padded to a common pitch in HBM.
+
+    points  : [rows, pitch, 2] float32/float64 CUDA tensor, (x, y) interleaved
+    lengths : [rows] int32 CUDA tensor of valid points per row, or None (= all full)
+    """
+    points: torch.Tensor
+    lengths: Optional[torch.Tensor] = None
+
+    def __post_init__(self):
+        p = self.points
+        if p.dim() != 3 or p.shape[2] != 2:
+            raise ValueError(f"points must be [rows, pitch, 2], got {tuple(p.shape)}")
+        if p.dtype not in _DTYPES:
+            raise ValueError("points must be float32 or float64")
+        _require_cuda(p, "points")
+        if self.lengths is not None:
+            l = self.lengths
+            if l.dtype != torch.int32 or l.dim() != 1 or l.shape[0] != p.shape[0]:
+                raise ValueError("lengths must be int32 [rows]")
+            _require_cuda(l, "lengths")
+
+    @property
+    def rows(self) -> int:
+        return int(self.points.shape[0])
+
+    @property
+    def pitch(self) -> int:
+        return int(self.points.shape[1])
+
+    def slice_rows(self, start: int, stop: Optional[int] = None) -> "ScanTable":
+        """Row view sharing memory (e.g. rows 1.. as the sources of sequence odometry)."""
+        pts = self.points[start:stop]
+        lens = None if self.lengths is None else self.lengths[start:stop]
+        return ScanTable(pts, lens)
+
+    @staticmethod
+    def pack_host(scans: Sequence[np.ndarray], dtype=np.float64, pitch: Optional[int] = None,
+                  pin: bool = False):
+        """Pad a list of (Ni, >=2) arrays into host tensors (points, lengths)."""
+        n = len(scans)
+        longest = max((len(s) for s in scans), default=1)
+        pitch = max(1, longest) if pitch is None else int(pitch)
+        if longest > pitch:
+            raise ValueError(f"scan with {longest} points does not fit pitch {pitch}")
+        pts = np.zeros((n, pitch, 2), dtype=dtype)
+        lens = np.zeros(n, dtype=np.int32)
+        for i, s in enumerate(scans):
+            s = np.asarray(s)
+            if s.size:
+                pts[i, : len(s)] = s[:, :2]
+            lens[i] = len(s)
+        tp, tl = torch.from_numpy(pts), torch.from_numpy(lens)
+        if pin:
+            tp, tl = tp.pin_memory(), tl.pin_memory()
+        return tp, tl
+
+    @staticmethod
+    def from_list(scans: Sequence[np.ndarray], dtype=np.float64, device="cuda",
+                  pitch: Optional[int] = None) -> "ScanTable":
+        tp, tl = ScanTable.pack_host(scans, dtype, pitch)
+        return ScanTable(tp.to(device), tl.to(device))
+
+
+@dataclass
+class AlignResult:
+    """Device tensors, one row per pair.  Poses are [R00 R01 R10 R11 tx ty]."""
+    pose_total: torch.Tensor          # cumulative: src_final = R A + t
+    pose_last: torch.Tensor           # last increment: what the reference icp() returns
+    error: torch.Tensor               # lagged mean NN distance (icp.py:48)
+    rmse: torch.Tensor
+    inliers: torch.Tensor
+    iterations: torch.Tensor
+    indices: Optional[torch.Tensor] = None
+    src_final: Optional[torch.Tensor] = None
+    index_history: Optional[torch.Tensor] = None
+
+    def rotation(self, which: str = "total") -> torch.Tensor:
+        p = self.pose_total if which == "total" else self.pose_last
+        return p[:, :4].reshape(-1, 2, 2)
+
+    def translation(self, which: str = "total") -> torch.Tensor:
+        p = self.pose_total if which == "total" else self.pose_last
+        return p[:, 4:6]
+
+    def theta(self, which: str = "total") -> torch.Tensor:
+        p = self.pose_total if which == "total" else self.pose_last
+        return torch.atan2(p[:, 2], p[:, 0])
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream) -> C.c_void_p:
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def _problem(src: ScanTable, tgt: ScanTable, pairing: str, src_row, tgt_row, first_pair: int):
+    if src.points.dtype != tgt.points.dtype:
+        raise ValueError("source and target tables must share a dtype")
+    if src.points.device != tgt.points.device:
+        raise ValueError("source and target tables must live on the same device")
+    pr = _cabi.Problem()
+    pr.src_points = src.points.data_ptr()
+    pr.tgt_points = tgt.points.data_ptr()
+    pr.src_len = None if src.lengths is None else src.lengths.data_ptr()
+    pr.tgt_len = None if tgt.lengths is None else tgt.lengths.data_ptr()
+    pr.src_pitch, pr.tgt_pitch = src.pitch, tgt.pitch
+    pr.dtype = _DTYPES[src.points.dtype]
+    pr.pairing = _PAIRINGS[pairing]
+    if pairing == "explicit":
+        for name, t in (("src_row", src_row), ("tgt_row", tgt_row)):
+            if t is None or t.dtype != torch.int32:
+                raise ValueError(f"{name} must be an int32 CUDA tensor for explicit pairing")
+            _require_cuda(t, name)
+        pr.src_row, pr.tgt_row = src_row.data_ptr(), tgt_row.data_ptr()
+    if pairing == "triangle":
+        if src.points.data_ptr() != tgt.points.data_ptr():
+            raise ValueError("triangle pairing enumerates pairs of ONE table")
+        pr.n_rows = src.rows
+        pr.first_pair = int(first_pair)
+    return pr
+
+
+def _default_pairs(src, tgt, pairing, src_row, first_pair):
+    if pairing == "rowwise":
+        return min(src.rows, tgt.rows)
+    if pairing == "explicit":
+        return int(src_row.shape[0])
+    r = src.rows
+    return r * (r - 1) // 2 - int(first_pair)
+
+
+def nn_search(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
+              pairing: str = "rowwise", src_row=None, tgt_row=None, first_pair: int = 0,
+              want_dist2: bool = True, out_idx=None, out_dist2=None, stream=None):
+    """Nearest target index for every source point of every pair.
+
+    Replaces ``KDTree(B).query(src)`` (icp.py:37-38): returns (idx int32 [B,pitch],
+    dist2 float64 [B,pitch] or None); idx = -1 beyond a row's length.
+    """
+    pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
+    b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
+    dev = src.points.device
+    idx = out_idx if out_idx is not None else torch.empty((b, src.pitch), dtype=torch.int32, device=dev)
+    d2 = out_dist2
+    if d2 is None and want_dist2:
+        d2 = torch.empty((b, src.pitch), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().b200icp_nn_batch(C.byref(pr), b, _ptr(idx), _ptr(d2), _stream_ptr(stream))
+    _cabi.check(rc, "b200icp_nn_batch")
+    return idx, d2
+
+
+def alloc_outputs(n_pairs: int, src_pitch: int, device, *, max_iterations: int = 0,
+                  want_indices=False, want_src=False, want_history=False) -> AlignResult:
+    f64 = dict(dtype=torch.float64, device=device)
+    i32 = dict(dtype=torch.int32, device=device)
+    return AlignResult(
+        pose_total=torch.empty((n_pairs, 6), **f64),
+        pose_last=torch.empty((n_pairs, 6), **f64),
+        error=torch.empty(n_pairs, **f64),
+        rmse=torch.empty(n_pairs, **f64),
+        inliers=torch.empty(n_pairs, **i32),
+        iterations=torch.empty(n_pairs, **i32),
+        indices=torch.empty((n_pairs, src_pitch), **i32) if want_indices else None,
+        src_final=torch.empty((n_pairs, src_pitch, 2), **f64) if want_src else None,
+        index_history=(torch.full((n_pairs, max_iterations, src_pitch), -1, **i32)
+                       if want_history else None),
+    )
+
+
+def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
+                pairing: str = "rowwise", src_row=None, tgt_row=None, first_pair: int = 0,
+                max_iterations: int = 20, tolerance: float = 1e-5,
+                init_pose: Optional[torch.Tensor] = None, max_corr_dist: Optional[float] = None,
+                want_indices: bool = False, want_src: bool = False, want_history: bool = False,
+                out: Optional[AlignResult] = None, stream=None) -> AlignResult:
+    """Run the whole ICP loop of every pair on the device (one kernel launch).
+
+    Replaces ``icp(A, B, max_iterations, tolerance)`` (icp.py:28-53) for a batch:
+    same defaults, same convergence rule, same lagged error.  ``init_pose`` is
+    [B,6] float64 (R row-major, t); ``max_corr_dist`` None = exactly the reference.
+    """
+    pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
+    b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
+    dev = src.points.device
+    if out is None:
+        out = alloc_outputs(b, src.pitch, dev, max_iterations=max_iterations,
+                            want_indices=want_indices, want_src=want_src, want_history=want_history)
+    opt = _cabi.Options()
+    opt.max_iterations = int(max_iterations)
+    opt.tolerance = float(tolerance)
+    opt.max_corr_dist = 0.0 if max_corr_dist is None else float(max_corr_dist)
+    if init_pose is not None:
+        if init_pose.dtype != torch.float64 or tuple(init_pose.shape) != (b, 6):
+            raise ValueError("init_pose must be float64 [n_pairs, 6]")
+        _require_cuda(init_pose, "init_pose")
+        opt.init_pose = init_pose.data_ptr()
+    o = _cabi.Outputs()
+    o.pose_total, o.pose_last = out.pose_total.data_ptr(), out.pose_last.data_ptr()
+    o.error, o.rmse = out.error.data_ptr(), out.rmse.data_ptr()
+    o.inliers, o.iterations = out.inliers.data_ptr(), out.iterations.data_ptr()
+    o.indices = None if out.indices is None else out.indices.data_ptr()
+    o.src_final = None if out.src_final is None else out.src_final.data_ptr()
+    o.index_history = None if out.index_history is None else out.index_history.data_ptr()
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().b200icp_align_batch(C.byref(pr), b, C.byref(opt), C.byref(o),
+                                             _stream_ptr(stream))
+    _cabi.check(rc, "b200icp_align_batch")
+    return out
+
+
+def polar_to_cartesian(raw: torch.Tensor, raw_len: Optional[torch.Tensor] = None,
+                       out_pitch: Optional[int] = None, stream=None) -> ScanTable:
+    """Device scan preparation (process.py:38-52): raw [S, pitch, 3] float64 rows of
+    (quality, angle_deg, distance_mm) -> filtered Cartesian ScanTable (float64)."""
+    if raw.dim() != 3 or raw.shape[2] != 3 or raw.dtype != torch.float64:
+        raise ValueError("raw must be float64 [scans, pitch, 3]")
+    _require_cuda(raw, "raw")
+    s, pitch = int(raw.shape[0]), int(raw.shape[1])
+    out_pitch = pitch if out_pitch is None else int(out_pitch)
+    xy = torch.empty((s, out_pitch, 2), dtype=torch.float64, device=raw.device)
+    lens = torch.empty(s, dtype=torch.int32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        rc = _cabi.lib().b200icp_polar_to_cartesian(_ptr(raw), _ptr(raw_len), s, pitch, _ptr(xy),
+                                                    _ptr(lens), out_pitch, _stream_ptr(stream))
+    _cabi.check(rc, "b200icp_polar_to_cartesian")
+    return ScanTable(xy, lens)
+
+
+def ffma_probe(inner_iters: int = 4096, repeats: int = 5, device="cuda") -> float:
+    """Measured FP32 FFMA throughput in TFLOP/s (roofline denominator of the NN phase)."""
+    sink = torch.zeros(4, dtype=torch.float32, device=device)
+    flop = C.c_int64(0)
+    best = 0.0
+    with torch.cuda.device(sink.device):
+        for _ in range(repeats + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = _cabi.lib().b200icp_ffma_probe(_ptr(sink), inner_iters, C.byref(flop), _stream_ptr(None))
+            e1.record()
+            _cabi.check(rc, "b200icp_ffma_probe")
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = max(best, flop.value / (ms * 1e-3) / 1e12)
+    return best

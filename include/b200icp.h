@@ -1,0 +1,162 @@
+/*
+ * b200icp.h -- C ABI of the B200-native 2D ICP scan-matching path.
+ *
+ * Drop-in boundary for the reference's registration step
+ * (DucVuUET04/ICP_SLAM-YOLO).  The reference has no FFI of its own: the boundary
+ * is the Python call  icp(A, B, max_iterations, tolerance) -> (src, R, t)
+ * (labels_segmentation/icp.py:28-53) built on best_fit_transform
+ * (labels_segmentation/icp.py:5-26), fed by polar_to_cartesian_3d
+ * (duc/ICP_LIDAR/process.py:38-52), plus the Open3D-shaped sibling
+ * gicp(points1, points2, threshold, voxel, trans_init) -> (rmse, T4x4)
+ * (duc/ICP_LIDAR/gicp_lidar.py:12-36, called at duc/ICP_LIDAR/mainn.py:311).
+ * Every entry point below names the reference lines it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - All data pointers are DEVICE pointers owned by the caller (host pointers only
+ *     where a parameter says "host").  The library allocates nothing, never writes
+ *     its inputs, and is asynchronous on the CUDA stream passed as `stream`
+ *     (a cudaStream_t cast to void*; NULL = legacy default stream).
+ *   - Every call returns a b200icp_status (0 = OK).  No exceptions, no aborts.
+ *     b200icp_last_error() returns a thread-local description of the last failure.
+ *   - Degenerate pairs (no source or no target points, every correspondence gated
+ *     out) do not fail the batch: they yield R = I, t = 0 (or the initial pose),
+ *     error = +inf, iterations = number of completed updates.
+ *   - Points are interleaved (x, y) pairs, float32 or float64.  All O(N) state
+ *     (source points, sums, poses, errors) is float64 on the device; only the
+ *     O(N*M) candidate search runs in float32 and every candidate is re-decided
+ *     in float64, so correspondence indices equal a float64 brute-force argmin
+ *     with lowest-index tie-break.
+ */
+#ifndef B200ICP_H_
+#define B200ICP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ICP_VERSION_MAJOR 0
+#define B200ICP_VERSION_MINOR 1
+
+typedef enum b200icp_status {
+  B200ICP_OK = 0,
+  B200ICP_ERR_INVALID_ARGUMENT = 1, /* NULL / negative size / bad enum            */
+  B200ICP_ERR_UNSUPPORTED_SHAPE = 2,/* pitch beyond what the fused kernel handles  */
+  B200ICP_ERR_CUDA = 3,             /* a CUDA runtime call failed (see last_error) */
+  B200ICP_ERR_NO_DEVICE = 4         /* no sm_100 device / driver                   */
+} b200icp_status;
+
+typedef enum b200icp_dtype { B200ICP_F32 = 0, B200ICP_F64 = 1 } b200icp_dtype;
+
+/* How pair p of a batch picks its source and target rows. */
+typedef enum b200icp_pairing {
+  B200ICP_PAIR_ROWWISE = 0,   /* src row p        , tgt row p                        */
+  B200ICP_PAIR_EXPLICIT = 1,  /* src row src_row[p], tgt row tgt_row[p]               */
+  B200ICP_PAIR_TRIANGLE = 2   /* q = first_pair + p enumerates (i < j) row-major over
+                                 n_rows rows of ONE table: tgt = row i, src = row j
+                                 (all-pairs loop-closure candidates)                  */
+} b200icp_pairing;
+
+/*
+ * A batch of ICP problems over row tables of ragged scans in HBM.
+ *   src_points : [src_rows][src_pitch][2]   tgt_points : [tgt_rows][tgt_pitch][2]
+ *   src_len / tgt_len : valid points per row (NULL => every row is full, = pitch)
+ * Sequence odometry (scan k+1 -> scan k, icp.py:28 called per consecutive pair) is
+ * ROWWISE with src_points = table + one row and tgt_points = table.
+ * Replaces the A, B arguments of icp() (labels_segmentation/icp.py:28).
+ */
+typedef struct b200icp_problem {
+  const void* src_points;
+  const void* tgt_points;
+  const int32_t* src_len;
+  const int32_t* tgt_len;
+  int32_t src_pitch;        /* points per source row (>= every src_len)            */
+  int32_t tgt_pitch;
+  int32_t dtype;            /* b200icp_dtype of BOTH point tables                  */
+  int32_t pairing;          /* b200icp_pairing                                     */
+  const int32_t* src_row;   /* EXPLICIT only                                       */
+  const int32_t* tgt_row;   /* EXPLICIT only                                       */
+  int64_t first_pair;       /* TRIANGLE only: linear index of this shard's pair 0  */
+  int32_t n_rows;           /* TRIANGLE only: rows in the table                    */
+  int32_t reserved;
+} b200icp_problem;
+
+/* Replaces max_iterations / tolerance of icp() (icp.py:28) and adds the Open3D-shaped
+ * trans_init / max_correspondence_distance of gicp() (gicp_lidar.py:12,29-34). */
+typedef struct b200icp_options {
+  int32_t max_iterations;   /* icp.py:28,35; reference default 20                   */
+  int32_t reserved;
+  double tolerance;         /* icp.py:49; < 0 forces all iterations                 */
+  double max_corr_dist;     /* <= 0 or +inf: no gate (exactly the reference);
+                               else keep pairs with distance < max_corr_dist        */
+  const double* init_pose;  /* NULL or [n_pairs][6] = R00 R01 R10 R11 tx ty         */
+} b200icp_options;
+
+/* Any pointer except pose_total / error / iterations may be NULL. */
+typedef struct b200icp_outputs {
+  double* pose_total;   /* [n_pairs][6] cumulative R,t with src_final = R A + t          */
+  double* pose_last;    /* [n_pairs][6] last increment: what icp() returns (icp.py:53)   */
+  double* error;        /* [n_pairs] mean NN distance of the last search (icp.py:48)     */
+  double* rmse;         /* [n_pairs] sqrt(mean d^2) over inliers of the last search      */
+  int32_t* inliers;     /* [n_pairs] correspondences used by the last update             */
+  int32_t* iterations;  /* [n_pairs] i+1 at break else max_iterations (icp.py:35,50)     */
+  int32_t* indices;     /* [n_pairs][src_pitch] correspondences of the last search       */
+  double* src_final;    /* [n_pairs][src_pitch][2] transformed source (icp.py:45,53)     */
+  int32_t* index_history; /* [n_pairs][max_iterations][src_pitch] (diagnostics/parity)   */
+} b200icp_outputs;
+
+/* ---- library ---------------------------------------------------------------- */
+int b200icp_version(void);               /* major*1000 + minor                     */
+const char* b200icp_last_error(void);    /* thread-local, never NULL               */
+
+/* Largest pitches the fused per-pair kernel accepts (host query). */
+int b200icp_max_src_pitch(void);
+int b200icp_max_tgt_pitch(void);
+
+/*
+ * Nearest-neighbour correspondence search, one search per pair.
+ * Replaces  tree = KDTree(B); distances, indices = tree.query(src)
+ * (labels_segmentation/icp.py:37-38).
+ *   idx_out   [n_pairs][src_pitch] int32, -1 beyond src_len
+ *   dist2_out [n_pairs][src_pitch] float64 squared distance (NULL to skip)
+ */
+int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs,
+                     int32_t* idx_out, double* dist2_out, void* stream);
+
+/*
+ * Whole ICP loop per pair, fused on the device (no host round trips).
+ * Replaces icp() (labels_segmentation/icp.py:28-53) including
+ * best_fit_transform() (icp.py:5-26).
+ */
+int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs,
+                        const b200icp_options* opt, const b200icp_outputs* out,
+                        void* stream);
+
+/*
+ * Scan preparation on the device: quality / range / front-arc filter and
+ * polar -> Cartesian with order-preserving compaction.
+ * Replaces polar_to_cartesian_3d (duc/ICP_LIDAR/process.py:38-52).
+ *   raw      [n_scans][raw_pitch][3] float64 rows (quality, angle_deg, distance_mm)
+ *   raw_len  [n_scans] valid rows per scan
+ *   xy_out   [n_scans][out_pitch][2] float64;  len_out [n_scans]
+ */
+int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_t n_scans,
+                               int32_t raw_pitch, double* xy_out, int32_t* len_out,
+                               int32_t out_pitch, void* stream);
+
+/*
+ * FP32 FFMA throughput probe used as the roofline denominator of the NN phase
+ * (MEASURED_PEAKS.json carries no FP32 figure).  Launches one kernel doing
+ * `flop_out[0]` floating point operations (written to a HOST int64); the caller
+ * times it with CUDA events on `stream`.  sink is a device float buffer of at
+ * least 1 element.
+ */
+int b200icp_ffma_probe(float* sink, int32_t inner_iters, int64_t* flop_out /*host*/,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ICP_H_ */

@@ -1,0 +1,284 @@
+"""NumPy/SciPy restatement of the reference's 2D point-to-point ICP path.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``) -- never imported by the product.
+
+Reference anchors (relative to /root/reference):
+  * ``labels_segmentation/icp.py:5-26``   best_fit_transform  -> :func:`best_fit_transform`
+  * ``labels_segmentation/icp.py:28-53``  icp                 -> :func:`icp_reference_form`
+  * ``duc/ICP_LIDAR/process.py:38-52``    polar_to_cartesian_3d -> :func:`polar_to_cartesian`
+  * ``duc/ICP_LIDAR/process.py:9-36``     load_and_prepare_scan -> :func:`load_and_prepare_scan`
+
+:func:`icp_extended` is the same loop with the bookkeeping the new call surface
+needs (per-iteration correspondence history, cumulative pose, lagged error,
+iteration count, optional initial pose and correspondence gate).  With
+``init_pose=None`` and ``max_corr_dist=None`` it performs the same floating
+point operations in the same order as the reference, so ``src`` is bitwise equal.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.spatial import KDTree
+
+
+# ----------------------------------------------------------------------------
+# best_fit_transform  (icp.py:5-26)
+# ----------------------------------------------------------------------------
+def best_fit_transform(P, Q):
+    """Least-squares rigid (R, t) taking matched rows of P onto Q.
+
+    icp.py:10-11 centroids, :13-14 centring, :16 H = PP^T QQ, :17 SVD,
+    :18 R = V U^T, :21-23 reflection repair on the last row of Vt, :25 t.
+    """
+    cP = np.mean(P, axis=0)
+    cQ = np.mean(Q, axis=0)
+    H = (P - cP).T @ (Q - cQ)
+    U, _, Vt = np.linalg.svd(H)
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        Vt[1, :] *= -1
+        R = Vt.T @ U.T
+    t = cQ.T - R @ cP.T
+    return R, t
+
+
+def best_fit_transform_closed_form(P, Q):
+    """Closed-form 2D Kabsch: theta = atan2(H01 - H10, H00 + H11).
+
+    Equals the proper-rotation SVD result of icp.py:17-23 to ~1e-16 rad
+    (SURVEY.md §8 a5); this is the form the CUDA kernel evaluates, restated
+    here so tests can separate "SVD vs closed form" from "CPU vs GPU".
+    """
+    cP = np.mean(P, axis=0)
+    cQ = np.mean(Q, axis=0)
+    H = (P - cP).T @ (Q - cQ)
+    num = H[0, 1] - H[1, 0]
+    den = H[0, 0] + H[1, 1]
+    hyp = math.hypot(num, den)
+    if hyp == 0.0:
+        c, s = 1.0, 0.0
+    else:
+        c, s = den / hyp, num / hyp
+    R = np.array([[c, -s], [s, c]])
+    t = cQ - R @ cP
+    return R, t
+
+
+# ----------------------------------------------------------------------------
+# icp  (icp.py:28-53), reference form: returns (src, R_last, t_last)
+# ----------------------------------------------------------------------------
+def icp_reference_form(A, B, max_iterations=20, tolerance=1e-5):
+    """Same signature and return as the reference's ``icp`` (icp.py:28)."""
+    res = icp_extended(A, B, max_iterations, tolerance)
+    return res.src, res.R_last, res.t_last
+
+
+@dataclass
+class IcpResult:
+    src: np.ndarray            # (N,2) transformed source            icp.py:45
+    R_last: np.ndarray         # last incremental rotation           icp.py:42,53 (quirk Q1)
+    t_last: np.ndarray
+    R_tot: np.ndarray          # cumulative pose: src = R_tot A + t_tot
+    t_tot: np.ndarray
+    error: float               # lagged mean NN distance             icp.py:48 (quirk Q2)
+    iterations: int            # i+1 at break else max_iterations    (quirk Q4)
+    rmse: float = float("nan")     # sqrt(mean d^2) over inliers, last search
+    fitness: float = float("nan")  # inliers / N, last search
+    indices: list = field(default_factory=list)   # per-iteration (N,) intp
+    errors: list = field(default_factory=list)    # per-iteration mean distance
+    inlier_masks: list = field(default_factory=list)
+
+
+def nn_kdtree(src, tgt):
+    """icp.py:37-38: tree rebuilt per call, k=1 Euclidean query."""
+    d, i = KDTree(tgt).query(src)
+    return d, i
+
+
+def nn_bruteforce(src, tgt, chunk=2048):
+    """float64 argmin_j |src_i - tgt_j|^2, lowest j on exact ties.
+
+    Stand-in for the KD-tree when M is huge; identical to ``KDTree.query`` on
+    all 1.86 M real queries of Scan_data_1.
+    """
+    src = np.asarray(src, dtype=np.float64)
+    tgt = np.asarray(tgt, dtype=np.float64)
+    n = src.shape[0]
+    idx = np.empty(n, dtype=np.intp)
+    d2 = np.empty(n, dtype=np.float64)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        dx = src[s:e, None, 0] - tgt[None, :, 0]
+        dy = src[s:e, None, 1] - tgt[None, :, 1]
+        dd = dx * dx + dy * dy
+        k = np.argmin(dd, axis=1)
+        idx[s:e] = k
+        d2[s:e] = dd[np.arange(e - s), k]
+    return np.sqrt(d2), idx
+
+
+def icp_extended(A, B, max_iterations=20, tolerance=1e-5, *, init_pose=None,
+                 max_corr_dist=None, nn="kdtree", solver="svd", keep_history=True):
+    """The reference loop (icp.py:32-53) plus bookkeeping.
+
+    init_pose      (R0 (2,2), t0 (2,)): pre-transforms A and is left-composed into
+                   the cumulative pose (Open3D ``trans_init`` convention,
+                   gicp_lidar.py:32).  PARITY-UNPINNED extension (Q7).
+    max_corr_dist  finite => only pairs with distance < max_corr_dist enter the
+                   fit and the error mean (Open3D ``max_correspondence_distance``
+                   shape).  PARITY-UNPINNED extension (Q5).  If no pair survives
+                   the loop stops: that search is not counted, error = +inf.
+    """
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    search = nn_kdtree if nn == "kdtree" else nn_bruteforce
+    fit = best_fit_transform if solver == "svd" else best_fit_transform_closed_form
+
+    src = np.copy(A)                                   # icp.py:32
+    R_tot = np.eye(2)
+    t_tot = np.zeros(2)
+    if init_pose is not None:
+        R0 = np.asarray(init_pose[0], dtype=np.float64)
+        t0 = np.asarray(init_pose[1], dtype=np.float64)
+        src = (R0 @ src.T).T + t0
+        R_tot, t_tot = R0.copy(), t0.copy()
+    prev_error = 0                                     # icp.py:33 (quirk Q3)
+    res = IcpResult(src, np.eye(2), np.zeros(2), R_tot, t_tot, float("inf"), 0)
+
+    for i in range(max_iterations):                    # icp.py:35
+        dist, idx = search(src, B)                     # icp.py:37-38
+        if max_corr_dist is None:
+            keep = None
+            P, Q, dsel = src, B[idx], dist             # icp.py:39
+        else:
+            keep = dist < max_corr_dist
+            if not np.any(keep):
+                res.error = float("inf")
+                res.fitness = 0.0
+                break
+            P, Q, dsel = src[keep], B[idx[keep]], dist[keep]
+        R, t = fit(P, Q)                               # icp.py:42
+        src = (R @ src.T).T + t                        # icp.py:45
+        R_tot = R @ R_tot
+        t_tot = R @ t_tot + t
+        mean_error = np.mean(dsel)                     # icp.py:48
+        res.R_last, res.t_last = R, t
+        res.error = float(mean_error)
+        res.rmse = float(np.sqrt(np.mean(dsel * dsel)))
+        res.fitness = float(len(dsel)) / float(len(src))
+        res.iterations = i + 1
+        if keep_history:
+            res.indices.append(np.asarray(idx))
+            res.errors.append(float(mean_error))
+            res.inlier_masks.append(keep)
+        if np.abs(prev_error - mean_error) < tolerance:   # icp.py:49-50
+            break
+        prev_error = mean_error                        # icp.py:51
+
+    res.src, res.R_tot, res.t_tot = src, R_tot, t_tot
+    return res
+
+
+# ----------------------------------------------------------------------------
+# scan preparation  (process.py:9-52)
+# ----------------------------------------------------------------------------
+def polar_to_cartesian_loop(scan):
+    """Row loop as in process.py:38-52 (math.radians/cos/sin per kept row)."""
+    if scan is None or len(scan) == 0:
+        return np.array([])
+    out = []
+    for quality, angle, distance in scan:
+        front = (angle <= 135) or (angle >= 225)                       # :45
+        if distance > 1000 and distance < 9000 and quality > 10 and front:   # :46
+            a = math.radians(angle)
+            out.append([distance * math.cos(a), -distance * math.sin(a), 0.0])  # :47-50
+    return np.array(out)
+
+
+def polar_keep_mask(scan):
+    """Row filter of process.py:45-46."""
+    q, a, d = scan[:, 0], scan[:, 1], scan[:, 2]
+    return ((a <= 135) | (a >= 225)) & (d > 1000) & (d < 9000) & (q > 10)
+
+
+def polar_to_cartesian(scan):
+    """Vectorised process.py:38-52; bitwise equal to the row loop on all
+    1,831 Scan_data_1 files (checked in tests when the reference is present)."""
+    scan = np.asarray(scan, dtype=np.float64)
+    if scan.size == 0:
+        return np.zeros((0, 3))
+    rows = scan[polar_keep_mask(scan)]
+    rad = np.radians(rows[:, 1])      # == math.radians: x * (pi/180) in C doubles
+    x = rows[:, 2] * np.cos(rad)
+    y = -rows[:, 2] * np.sin(rad)
+    return np.stack([x, y, np.zeros_like(x)], axis=1)
+
+
+def scan_path(directory, k):
+    """Scan_data_1 mixes ``Scan_data_{k}.npy`` (k<=219) and ``scan_data_{k}.npy``
+    (SURVEY.md §8 a1); resolve either spelling."""
+    for stem in ("Scan_data_", "scan_data_", "scan_"):
+        p = os.path.join(directory, f"{stem}{k}.npy")
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def load_and_prepare_scan(path):
+    """process.py:9-36: (N,3) polar rows -> Cartesian, (N,2) -> append z=0,
+    anything else / missing file -> None."""
+    if path is None or not os.path.exists(path):
+        return None
+    try:
+        raw = np.load(path)
+        if raw.ndim != 2 or raw.shape[1] not in (2, 3):
+            return None
+        raw = np.asarray(raw, dtype=np.float64)
+        if raw.shape[1] == 3:
+            return polar_to_cartesian(raw)
+        return np.hstack((raw, np.zeros((raw.shape[0], 1))))
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------
+# synthetic workloads.  Kept here so that the
+# tests, the bench's CPU arm and the GPU arm all draw the *same* arrays.
+# ----------------------------------------------------------------------------
+def synth_room_pair(pair_index, n_points=360, dtype=np.float32):
+    """One scan pair of config 3: star-convex room, 1 degree beams, N(0,5mm)
+    range noise; source = same room seen after a small pose change.
+    ``seed = 1234 + pair_index`` (PCG64).  Returns (src, tgt, theta, t) with
+    src/tgt (n_points,2) of ``dtype`` (values generated in float64, then cast)."""
+    rng = np.random.Generator(np.random.PCG64(1234 + int(pair_index)))
+    amp = rng.uniform(0.0, 600.0, size=4)
+    psi = rng.uniform(0.0, 2.0 * np.pi, size=4)
+    theta = rng.uniform(-0.1, 0.1)
+    t = rng.uniform(-100.0, 100.0, size=2)
+    phi = np.deg2rad(np.arange(n_points, dtype=np.float64) * (360.0 / n_points))
+    k = np.arange(1, 5, dtype=np.float64)[:, None]
+
+    def room(ph):
+        return 3000.0 + np.sum(amp[:, None] * np.sin(k * ph[None, :] + psi[:, None]), axis=0)
+
+    r_t = room(phi) + rng.normal(0.0, 5.0, size=n_points)
+    tgt = np.stack([r_t * np.cos(phi), r_t * np.sin(phi)], axis=1)
+    # the source frame is rotated by theta and shifted by t relative to the target frame
+    r_s = room(phi + theta) + rng.normal(0.0, 5.0, size=n_points)
+    world = np.stack([r_s * np.cos(phi + theta), r_s * np.sin(phi + theta)], axis=1)
+    c, s = np.cos(theta), np.sin(theta)
+    Rm = np.array([[c, -s], [s, c]])
+    src = (world - t) @ Rm          # = R^T (world - t), rows
+    return src.astype(dtype), tgt.astype(dtype), theta, t
+
+
+def synth_room_batch(first_pair, count, n_points=360, dtype=np.float32):
+    src = np.empty((count, n_points, 2), dtype=dtype)
+    tgt = np.empty((count, n_points, 2), dtype=dtype)
+    for b in range(count):
+        s, t, _, _ = synth_room_pair(first_pair + b, n_points, dtype)
+        src[b], tgt[b] = s, t
+    return src, tgt

@@ -1,0 +1,59 @@
+"""Import the UNMODIFIED reference ``labels_segmentation/icp.py`` (build container only).
+
+TEST INFRASTRUCTURE.  ``/root/reference`` exists only in the build container,
+never on the GPU box; callers must check :func:`reference_available` first.
+The reference module imports ``matplotlib.pyplot`` (icp.py:2) and runs a demo
+with ``plt.show()`` at import time (icp.py:55-78); matplotlib is not installed
+here, so a no-op stub is registered for the duration of the import.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("ICP_REFERENCE_ROOT", "/root/reference")
+_ICP_PATH = os.path.join(REFERENCE_ROOT, "labels_segmentation", "icp.py")
+_cached = None
+
+
+def reference_available() -> bool:
+    return os.path.isfile(_ICP_PATH)
+
+
+def scan_dir(name="Scan_data_1") -> str:
+    return os.path.join(REFERENCE_ROOT, name)
+
+
+def load_reference_icp():
+    """Returns the reference module: ``.icp``, ``.best_fit_transform`` and the
+    demo globals ``A, B, A_aligned, R_est, t_est`` (icp.py:57-67)."""
+    global _cached
+    if _cached is not None:
+        return _cached
+    if not reference_available():
+        raise FileNotFoundError(_ICP_PATH)
+
+    def _noop(*a, **k):
+        return None
+
+    saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot")}
+    mpl = types.ModuleType("matplotlib")
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.__getattr__ = lambda name: _noop        # figure/scatter/legend/... -> no-op
+    mpl.pyplot = plt
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = plt
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_icp", _ICP_PATH)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached = mod
+    return mod
