@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native 2D ICP path.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): batched
+synthetic 2D LiDAR pairs, 65,536 pairs x 360 points, 30 forced iterations
+(tolerance = -1 so the work is deterministic), float32 point tables generated in float64
+by oracle.icp_oracle.synth_room_batch (seed = 1234 + pair index).  Weak scaling: every
+rank aligns its own 65,536 pairs (pair indices rank*65536 ...), no data-path collective.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference      # CPU arm: the oracle port on all host cores
+
+One JSON line on stdout (rank 0).  A "step" = one pass of the fused ICP kernel over the
+rank's whole batch (one launch).  `value` = alignments/s with inputs resident in HBM;
+`e2e` = the same through HostPipeline (pinned host buffers, H2D + D2H inside the timed
+region); `roofline` = algorithmic FP32 FLOP/s of the search (5 FLOP per pair-eval,
+SURVEY.md §8d) over the FFMA peak measured live by the library's probe kernel.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 360
+ITERS = 30
+FLOP_PER_PAIR_EVAL = 5.0
+PAIR_EVALS_PER_ALIGNMENT = N_POINTS * N_POINTS * ITERS
+ALG_BYTES_PER_ALIGNMENT = 2 * N_POINTS * 8 + 12 + 36   # 5,808 B
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=65536, help="pairs per GPU (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (NumPy + SciPy KD-tree + LAPACK SVD, as the reference computes it)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    first, count = args
+    from oracle import icp_oracle as orc
+    src, tgt = orc.synth_room_batch(first, count)
+    src64, tgt64 = src.astype(np.float64), tgt.astype(np.float64)
+    t0 = time.perf_counter()
+    its = 0
+    for p in range(count):
+        r = orc.icp_extended(src64[p], tgt64[p], ITERS, -1.0, keep_history=False)
+        its += r.iterations
+    return time.perf_counter() - t0, its
+
+
+def cpu_throughput(sample_pairs, cores):
+    """alignments/s of the oracle port over `sample_pairs` pairs spread on `cores` processes
+    (wall time of the ICP calls only; generation excluded)."""
+    import multiprocessing as mp
+    per = max(1, sample_pairs // cores)
+    jobs = [(i * per, per) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 1)] * cores)          # warm the workers (imports)
+        t0 = time.perf_counter()
+        out = pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+    busy = max(o[0] for o in out)
+    n = per * cores
+    assert all(o[1] == per * ITERS for o in out)
+    return n / busy, n, wall
+
+
+def default_cpu_sample(cores):
+    """~15 s of single-core work (15 ms per 360x360x30 alignment), a multiple of the core count."""
+    return max(1024 // cores, 4) * cores
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or default_cpu_sample(cores)
+    steps_ms, vals = [], []
+    for i in range(args.warmup + args.steps):
+        v, n, wall = cpu_throughput(sample, cores)
+        if i >= args.warmup:
+            vals.append(v)
+            steps_ms.append(1e3 * n / v)
+    value = float(np.mean(vals))
+    desc = f"{sample} pairs x {N_POINTS} pts x {ITERS} forced iterations per step, {cores} processes"
+    line = {
+        "impl": "reference", "metric": "ICP alignments/sec (360-pt 2D scans, 30 iters)",
+        "value": value, "unit": "alignments/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(steps_ms)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "nn_pairs_per_s": value * PAIR_EVALS_PER_ALIGNMENT,
+        "config": {"workload": "configs[2]: batched synthetic 2D LiDAR pairs, 360 x 360 points, 30 forced "
+                               "iterations (tolerance=-1)", "sample_pairs_per_step": sample,
+                   "implementation": "oracle port of labels_segmentation/icp.py:5-53 (NumPy mean/SVD + SciPy "
+                                     "KDTree rebuilt every iteration); the reference is pure Python and cannot "
+                                     "travel to the GPU box", "cpu": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import icp_slam_yolo_b200 as m
+    from oracle import icp_oracle as orc          # input generator + CPU baseline only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # CPU baseline first: its worker processes are forked before CUDA is initialised
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or default_cpu_sample(cores)
+        v, n, wall = cpu_throughput(sample, cores)
+        cpu_base = {
+            "value": v, "unit": "alignments/s", "cores": cores, "kind": "port",
+            "sample": f"{n} pairs of the same workload (360 x 360 x 30 forced iterations) on {cores} "
+                      f"processes, oracle port of icp.py:5-53 (SciPy KDTree + NumPy SVD); {cpu_model()}"}
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m.lib()                                        # fail loudly if the CUDA library is missing
+
+    P = args.pairs
+    first = rank * P
+    src_np, tgt_np = orc.synth_room_batch(first, P)              # float32, values generated in float64
+    h_src = torch.from_numpy(src_np).pin_memory()
+    h_tgt = torch.from_numpy(tgt_np).pin_memory()
+    src = m.ScanTable(h_src.to(dev))
+    tgt = m.ScanTable(h_tgt.to(dev))
+    out = m.alloc_outputs(P, N_POINTS, dev)
+
+    def step():
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, out=out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # FP32 peak of this GPU, measured live (MEASURED_PEAKS.json has no FP32 figure)
+    fp32_peak = m.ffma_probe()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        e1.record()
+    t_all1.record()
+    barrier()
+    total_ms = max_over_ranks(t_all0.elapsed_time(t_all1))
+    kernel_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs]))     # per-launch duration
+    clocks = sampler.stop() if rank == 0 else None
+    assert bool(torch.all(out.iterations == ITERS)), "forced-iteration run did not run 30 iterations"
+
+    ms_per_step = total_ms / args.steps
+    value = world * P / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host buffers -> chunked H2D || kernel || D2H, through HostPipeline
+    e2e = None
+    if not args.no_e2e:
+        pipe = m.registration.HostPipeline(P, N_POINTS, N_POINTS, dtype=torch.float32, chunks=16, device=dev)
+        for _ in range(2):
+            pipe.run(h_src, h_tgt, max_iterations=ITERS, tolerance=-1.0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            hp, he, hi = pipe.run(h_src, h_tgt, max_iterations=ITERS, tolerance=-1.0)
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        assert torch.equal(hp, out.pose_total.cpu()), "e2e results differ from the resident-input run"
+        h2d, d2h = pipe.bytes_per_run(ragged=False)
+        e2e = {"value": world * P / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "launches_per_step": pipe.launches,
+               "api": "icp_slam_yolo_b200.registration.HostPipeline.run (16 chunks, copy/compute overlap)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops = P * PAIR_EVALS_PER_ALIGNMENT * FLOP_PER_PAIR_EVAL
+    achieved_tflops = flops / (kernel_ms * 1e-3) / 1e12
+    hbm_peak, hbm_src = measured_hbm_peak()
+    achieved_gbs = P * ALG_BYTES_PER_ALIGNMENT / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": "ICP alignments/sec (360-pt 2D scans, 30 iters)",
+        "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 search + f64 state", "data": "synthetic",
+        "nn_pairs_per_s": value * PAIR_EVALS_PER_ALIGNMENT,
+        "config": {"workload": "configs[2]: batched synthetic 2D LiDAR pairs, %d pairs per GPU x 360 x 360 "
+                               "points, 30 forced iterations (tolerance=-1), float32 tables" % P,
+                   "pairs_per_gpu": P, "points": N_POINTS, "iterations": ITERS,
+                   "l2": "inputs (%.0f MB per GPU) exceed the 126 MB L2; no flush needed" %
+                         (P * N_POINTS * 16 / 1e6),
+                   "parallelism": "pairs sharded by contiguous index range, no collective"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32", "kernel": "icp_align_kernel<3>", "achieved": achieved_tflops,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
+                     "peak_source": "b200icp_ffma_probe measured live (dependent-FFMA chains, all SMs)",
+                     "algorithmic_flop_per_launch": flops, "kernel_ms": kernel_ms, "traffic": None,
+                     "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                             "algorithmic_bytes_per_launch": P * ALG_BYTES_PER_ALIGNMENT}},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -400,14 +400,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
       nn_candidates<S>(ntx, nty, ngroups, fx, fy, c);
       double d2[S];
       nn_resolve<S>(t64, m, c, sx, sy, valid, tmax, lane, idx, d2);
-      if (out.index_history) {
-        int32_t* h = out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch;
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-          const int i = tid + k * nthreads;
-          if (i < pr.src_pitch) h[i] = valid[k] ? idx[k] : -1;
-        }
-      }
       // ---- gather matches (icp.py:39), gate, first reduction: centroids + distance sums
       double bx[S], by[S];
       bool use[S];
@@ -431,6 +423,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
       if (cnt < 0.5) {            // every correspondence gated out: stop, search not counted
         err = CUDART_INF; rmse = CUDART_INF; inl = 0;
         break;
+      }
+      if (out.index_history) {
+        int32_t* h = out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          const int i = tid + k * nthreads;
+          if (i < pr.src_pitch) h[i] = valid[k] ? idx[k] : -1;
+        }
       }
       const double inv = 1.0 / cnt;
       const double cax = r1[0] * inv, cay = r1[1] * inv;       // icp.py:10

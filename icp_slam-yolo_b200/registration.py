@@ -277,3 +277,87 @@ def ffma_probe(inner_iters: int = 4096, repeats: int = 5, device="cuda") -> floa
             ms = e0.elapsed_time(e1)
             best = max(best, flop.value / (ms * 1e-3) / 1e12)
     return best
+
+
+class HostPipeline:
+    """End-to-end batched alignment from HOST buffers: the call a user with NumPy-side scans
+    makes.  Pinned host tables are streamed to the device in chunks on a copy stream while
+    the previous chunk's ICP kernel runs, and each chunk's poses / errors / iteration counts
+    are copied back to pinned host memory, so host<->device traffic overlaps the compute.
+
+    Device staging buffers and pinned result buffers are allocated once and reused.
+    """
+
+    def __init__(self, n_pairs: int, src_pitch: int, tgt_pitch: int, dtype=torch.float32,
+                 chunks: int = 8, device="cuda"):
+        self.n_pairs, self.src_pitch, self.tgt_pitch = int(n_pairs), int(src_pitch), int(tgt_pitch)
+        self.device = torch.device(device)
+        self.chunk = max(1, -(-self.n_pairs // max(1, chunks)))
+        self.dtype = dtype
+        c = self.chunk
+        mk = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, device=self.device)
+        self.bufs = [dict(src=mk(c, src_pitch, 2), tgt=mk(c, tgt_pitch, 2),
+                          slen=mk(c, dt=torch.int32), tlen=mk(c, dt=torch.int32),
+                          out=alloc_outputs(c, src_pitch, self.device)) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.out_stream = torch.cuda.Stream(device=self.device)
+        pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self.h_pose = pin(self.n_pairs, 6, dt=torch.float64)
+        self.h_error = pin(self.n_pairs, dt=torch.float64)
+        self.h_iters = pin(self.n_pairs, dt=torch.int32)
+        self.launches = 0
+
+    def bytes_per_run(self, ragged: bool):
+        elt = 4 if self.dtype == torch.float32 else 8
+        h2d = self.n_pairs * (self.src_pitch + self.tgt_pitch) * 2 * elt + (8 * self.n_pairs if ragged else 0)
+        d2h = self.n_pairs * (6 * 8 + 8 + 4)
+        return h2d, d2h
+
+    def run(self, h_src: torch.Tensor, h_tgt: torch.Tensor, h_src_len=None, h_tgt_len=None, *,
+            max_iterations: int = 20, tolerance: float = 1e-5, max_corr_dist=None):
+        """h_src [B,src_pitch,2], h_tgt [B,tgt_pitch,2] pinned host tensors (row-wise pairs).
+        Returns pinned host tensors (pose_total [B,6], error [B], iterations [B]); they are
+        valid after the returned event (or a device synchronize)."""
+        main = torch.cuda.current_stream(self.device)
+        ready = [None, None]       # compute-done events per staging buffer
+        drained = [None, None]     # results-copied events per staging buffer
+        self.launches = 0
+        n_chunks = -(-self.n_pairs // self.chunk)
+        for ci in range(n_chunks):
+            b0 = ci * self.chunk
+            b1 = min(self.n_pairs, b0 + self.chunk)
+            nb = b1 - b0
+            buf = self.bufs[ci & 1]
+            with torch.cuda.stream(self.copy_stream):
+                if ready[ci & 1] is not None:
+                    self.copy_stream.wait_event(ready[ci & 1])      # kernel finished reading it
+                buf["src"][:nb].copy_(h_src[b0:b1], non_blocking=True)
+                buf["tgt"][:nb].copy_(h_tgt[b0:b1], non_blocking=True)
+                if h_src_len is not None:
+                    buf["slen"][:nb].copy_(h_src_len[b0:b1], non_blocking=True)
+                    buf["tlen"][:nb].copy_(h_tgt_len[b0:b1], non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self.copy_stream)
+            main.wait_event(copied)
+            if drained[ci & 1] is not None:
+                main.wait_event(drained[ci & 1])                    # previous results left the buffer
+            s = ScanTable(buf["src"][:nb], buf["slen"][:nb] if h_src_len is not None else None)
+            t = ScanTable(buf["tgt"][:nb], buf["tlen"][:nb] if h_tgt_len is not None else None)
+            align_pairs(s, t, n_pairs=nb, max_iterations=max_iterations, tolerance=tolerance,
+                        max_corr_dist=max_corr_dist, out=buf["out"], stream=main)
+            self.launches += 1
+            done = torch.cuda.Event()
+            done.record(main)
+            ready[ci & 1] = done
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(done)
+                self.h_pose[b0:b1].copy_(buf["out"].pose_total[:nb], non_blocking=True)
+                self.h_error[b0:b1].copy_(buf["out"].error[:nb], non_blocking=True)
+                self.h_iters[b0:b1].copy_(buf["out"].iterations[:nb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.out_stream)
+                drained[ci & 1] = ev
+        for ev in drained:
+            if ev is not None:
+                main.wait_event(ev)
+        return self.h_pose, self.h_error, self.h_iters

@@ -249,36 +249,50 @@ def load_and_prepare_scan(path):
 # tests, the bench's CPU arm and the GPU arm all draw the *same* arrays.
 # ----------------------------------------------------------------------------
 def synth_room_pair(pair_index, n_points=360, dtype=np.float32):
-    """One scan pair of config 3: star-convex room, 1 degree beams, N(0,5mm)
-    range noise; source = same room seen after a small pose change.
-    ``seed = 1234 + pair_index`` (PCG64).  Returns (src, tgt, theta, t) with
-    src/tgt (n_points,2) of ``dtype`` (values generated in float64, then cast)."""
-    rng = np.random.Generator(np.random.PCG64(1234 + int(pair_index)))
-    amp = rng.uniform(0.0, 600.0, size=4)
-    psi = rng.uniform(0.0, 2.0 * np.pi, size=4)
-    theta = rng.uniform(-0.1, 0.1)
-    t = rng.uniform(-100.0, 100.0, size=2)
-    phi = np.deg2rad(np.arange(n_points, dtype=np.float64) * (360.0 / n_points))
-    k = np.arange(1, 5, dtype=np.float64)[:, None]
-
-    def room(ph):
-        return 3000.0 + np.sum(amp[:, None] * np.sin(k * ph[None, :] + psi[:, None]), axis=0)
-
-    r_t = room(phi) + rng.normal(0.0, 5.0, size=n_points)
-    tgt = np.stack([r_t * np.cos(phi), r_t * np.sin(phi)], axis=1)
-    # the source frame is rotated by theta and shifted by t relative to the target frame
-    r_s = room(phi + theta) + rng.normal(0.0, 5.0, size=n_points)
-    world = np.stack([r_s * np.cos(phi + theta), r_s * np.sin(phi + theta)], axis=1)
-    c, s = np.cos(theta), np.sin(theta)
-    Rm = np.array([[c, -s], [s, c]])
-    src = (world - t) @ Rm          # = R^T (world - t), rows
-    return src.astype(dtype), tgt.astype(dtype), theta, t
+    """One scan pair of config 3 (see :func:`synth_room_batch`): returns (src, tgt, theta, t)."""
+    src, tgt, theta, t = synth_room_batch(pair_index, 1, n_points, dtype, with_truth=True)
+    return src[0], tgt[0], float(theta[0]), t[0]
 
 
-def synth_room_batch(first_pair, count, n_points=360, dtype=np.float32):
-    src = np.empty((count, n_points, 2), dtype=dtype)
-    tgt = np.empty((count, n_points, 2), dtype=dtype)
+def synth_room_batch(first_pair, count, n_points=360, dtype=np.float32, with_truth=False):
+    """Config 3 generator: ``count`` scan pairs starting at ``first_pair``.
+
+    Target = n_points beams at equal angular spacing on a star-convex room
+    r(phi) = 3000 + sum_{k=1..4} a_k sin(k phi + psi_k) mm, a_k ~ U(0,600), psi_k ~ U(0,2pi),
+    plus N(0, 5 mm) range noise (no exact ties).  Source = the same room sampled at
+    phi + theta, expressed in a frame rotated by theta ~ U(-0.1,0.1) rad and shifted by
+    t ~ U(-100,100)^2 mm, with independent noise.  Pair b draws from
+    ``PCG64(1234 + first_pair + b)`` in a fixed order, so any batch split yields the same
+    values.  Generated in float64, cast to ``dtype``.  All math is elementwise (no BLAS), so
+    results do not depend on ``count``.
+    """
+    amp = np.empty((count, 4)); psi = np.empty((count, 4)); theta = np.empty(count)
+    t = np.empty((count, 2)); nz_t = np.empty((count, n_points)); nz_s = np.empty((count, n_points))
     for b in range(count):
-        s, t, _, _ = synth_room_pair(first_pair + b, n_points, dtype)
-        src[b], tgt[b] = s, t
+        rng = np.random.Generator(np.random.PCG64(1234 + int(first_pair) + b))
+        amp[b] = rng.uniform(0.0, 600.0, size=4)
+        psi[b] = rng.uniform(0.0, 2.0 * np.pi, size=4)
+        theta[b] = rng.uniform(-0.1, 0.1)
+        t[b] = rng.uniform(-100.0, 100.0, size=2)
+        nz_t[b] = rng.normal(0.0, 5.0, size=n_points)
+        nz_s[b] = rng.normal(0.0, 5.0, size=n_points)
+    phi = np.deg2rad(np.arange(n_points, dtype=np.float64) * (360.0 / n_points))[None, :]
+
+    def room(ph):                       # ph [count, n]
+        r = np.full(ph.shape, 3000.0)
+        for k in range(4):
+            r = r + amp[:, k:k + 1] * np.sin((k + 1.0) * ph + psi[:, k:k + 1])
+        return r
+
+    r_t = room(np.broadcast_to(phi, (count, n_points))) + nz_t
+    tgt = np.stack([r_t * np.cos(phi), r_t * np.sin(phi)], axis=2)
+    ph_s = phi + theta[:, None]
+    r_s = room(ph_s) + nz_s
+    wx = r_s * np.cos(ph_s) - t[:, 0:1]
+    wy = r_s * np.sin(ph_s) - t[:, 1:2]
+    c, s = np.cos(theta)[:, None], np.sin(theta)[:, None]
+    src = np.stack([wx * c + wy * s, wy * c - wx * s], axis=2)       # R^T (world - t)
+    src, tgt = src.astype(dtype), tgt.astype(dtype)
+    if with_truth:
+        return src, tgt, theta, t
     return src, tgt

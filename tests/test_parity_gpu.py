@@ -1,0 +1,327 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Bars (BASELINE.json north_star): correspondence indices bit-exact; R within 1e-5 rad and t
+within 1e-5 m = 1e-2 mm of the reference's NumPy/SciPy ICP.  The kernel keeps all O(N) state
+in float64, so the tests hold it to much tighter figures (stated per test).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import icp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-5        # rad  (north star)
+TRANS_TOL = 1e-2      # mm   (= 1e-5 m, north star)
+TIGHT_ROT = 1e-9      # what the float64 state actually delivers
+TIGHT_TRANS = 1e-6    # mm
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import icp_slam_yolo_b200 as m
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m.lib()           # fails loudly when the CUDA library is missing
+    return m
+
+
+def _theta(pose6):
+    return np.arctan2(pose6[..., 2], pose6[..., 0])
+
+
+class _Host:
+    """AlignResult copied to NumPy once (one sync instead of one per pair)."""
+    def __init__(self, res):
+        for f in ("pose_total", "pose_last", "error", "rmse", "inliers", "iterations", "indices",
+                  "src_final", "index_history"):
+            v = getattr(res, f)
+            setattr(self, f, None if v is None else v.cpu().numpy())
+
+
+def _check_pair(res, p, o, n, *, history=True, rot=TIGHT_ROT, trans=TIGHT_TRANS):
+    if not isinstance(res, _Host):
+        if not hasattr(res, "_host"):
+            res._host = _Host(res)
+        res = res._host
+    pt = res.pose_total[p]
+    assert int(res.iterations[p]) == o.iterations, f"pair {p}: iterations"
+    th_o = math.atan2(o.R_tot[1, 0], o.R_tot[0, 0])
+    assert abs(_theta(pt) - th_o) < rot, f"pair {p}: rotation"
+    assert np.max(np.abs(pt[4:6] - o.t_tot)) < trans, f"pair {p}: translation"
+    assert np.allclose(pt[:4].reshape(2, 2), o.R_tot, rtol=0, atol=rot)
+    if o.iterations:
+        assert abs(float(res.error[p]) - o.error) < 1e-9 * max(1.0, o.error), f"pair {p}: error"
+    if history and res.index_history is not None:
+        h = res.index_history[p]
+        for it, idx in enumerate(o.indices):
+            assert np.array_equal(h[it, :n], idx), f"pair {p}: indices differ at iteration {it}"
+        assert np.all(h[o.iterations:, :] == -1)
+    if res.indices is not None and o.iterations:
+        assert np.array_equal(res.indices[p, :n], o.indices[-1])
+    if res.src_final is not None:
+        assert np.allclose(res.src_final[p, :n], o.src, rtol=0, atol=trans)
+
+
+# ---------------------------------------------------------------------------------------
+# nearest-neighbour kernel (icp.py:37-38)
+# ---------------------------------------------------------------------------------------
+def test_nn_first_iteration_all_scan_pairs_bit_exact(b200, cart_scans):
+    table = b200.ScanTable.from_list(cart_scans)
+    idx, d2 = b200.nn_search(table.slice_rows(1), table.slice_rows(0, table.rows - 1))
+    idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
+    queries = 0
+    for p in range(len(cart_scans) - 1):
+        A, B = cart_scans[p + 1], cart_scans[p]
+        dist, ref_idx = orc.nn_kdtree(A, B)
+        assert np.array_equal(idx[p, :len(A)], ref_idx), f"pair {p}"
+        assert np.all(idx[p, len(A):] == -1)
+        assert np.allclose(np.sqrt(d2[p, :len(A)]), dist, rtol=1e-14, atol=0)
+        queries += len(A)
+    assert queries > 200000
+
+
+def test_nn_near_ties_and_exact_ties(b200):
+    """FP32 cannot separate these; the float64 re-decision must, lowest index on exact ties."""
+    rng = np.random.default_rng(5)
+    n, m = 300, 256
+    B = rng.uniform(-8000, 8000, size=(m, 2))
+    A = np.empty((n, 2))
+    for i in range(n):          # sources almost equidistant from two targets
+        a, b = rng.choice(m, 2, replace=False)
+        mid = 0.5 * (B[a] + B[b])
+        A[i] = mid + (B[a] - B[b]) * rng.uniform(-1e-10, 1e-10)
+    B2 = np.concatenate([B, B[:64]])              # exact duplicates: ties -> lowest index
+    for src, tgt in ((A, B), (A, B2), (B[:128] + 1e-7, B2)):
+        s = b200.ScanTable.from_list([src])
+        t = b200.ScanTable.from_list([tgt])
+        idx, _ = b200.nn_search(s, t)
+        _, ref = orc.nn_bruteforce(src, tgt)
+        assert np.array_equal(idx[0, :len(src)].cpu().numpy(), ref)
+
+
+def test_nn_shapes_ragged_and_limits(b200):
+    rng = np.random.default_rng(11)
+    cases = [(1, 1), (1, 7), (5, 1), (31, 33), (32, 8), (33, 9), (129, 257), (385, 77),
+             (513, 1025), (1024, 4096), (1000, 4095)]
+    for n, m in cases:
+        A = rng.normal(0, 3000, size=(n, 2))
+        B = rng.normal(0, 3000, size=(m, 2))
+        for dt in (np.float64, np.float32):
+            s = b200.ScanTable.from_list([A], dtype=dt)
+            t = b200.ScanTable.from_list([B], dtype=dt)
+            idx, d2 = b200.nn_search(s, t)
+            dist, ref = orc.nn_bruteforce(A.astype(dt), B.astype(dt))
+            assert np.array_equal(idx[0].cpu().numpy(), ref), (n, m, dt)
+            assert np.allclose(np.sqrt(d2[0].cpu().numpy()), dist, rtol=1e-14)
+
+
+def test_nn_empty_rows_and_bad_shapes(b200):
+    A = [np.zeros((0, 2)), np.array([[1.0, 2.0]]), np.array([[0.0, 0.0], [5.0, 5.0]])]
+    B = [np.array([[1.0, 1.0]]), np.zeros((0, 2)), np.array([[4.0, 4.0], [1.0, 0.0]])]
+    s, t = b200.ScanTable.from_list(A), b200.ScanTable.from_list(B)
+    idx, d2 = b200.nn_search(s, t)
+    idx = idx.cpu().numpy()
+    assert np.all(idx[0] == -1) and np.all(idx[1] == -1)
+    assert list(idx[2]) == [1, 0]
+    big = b200.ScanTable(torch.zeros((1, 1025, 2), dtype=torch.float64, device="cuda"))
+    with pytest.raises(b200.B200IcpError, match="UNSUPPORTED_SHAPE"):
+        b200.nn_search(big, t.slice_rows(0, 1))
+    with pytest.raises(b200.B200IcpError):
+        b200.ScanTable(torch.zeros((1, 4, 2), dtype=torch.float64))       # CPU tensor: no fallback
+
+
+# ---------------------------------------------------------------------------------------
+# fused ICP loop (icp.py:28-53)
+# ---------------------------------------------------------------------------------------
+def test_circle_demo_known_answer(b200, golden):
+    """icp.py:55-67.  Targets 0 and 49 of the demo coincide to 2.4e-16, so on that one
+    near-exact tie SciPy's pick is undefined; poses must still agree."""
+    A, B = golden["demo_A"], golden["demo_B"]
+    o = orc.icp_extended(A, B)
+    r = b200.icp_full(A, B)
+    assert r.iterations == o.iterations == 7
+    assert np.allclose(r.src, golden["demo_A_aligned"], rtol=0, atol=1e-12)
+    assert np.allclose(r.R_last, golden["demo_R_est"], atol=1e-12)
+    assert np.allclose(r.t_last, golden["demo_t_est"], atol=1e-12)
+    same = (r.indices % 49) == (o.indices[-1] % 49)
+    assert np.all(same)
+    src, R, t = b200.icp(A, B)                      # reference-form return (quirk Q1)
+    assert np.allclose(src, golden["demo_A_aligned"], atol=1e-12) and R.shape == (2, 2) and t.shape == (2,)
+
+
+def test_scan_data_1_all_pairs_full_history(b200, cart_scans, oracle_pairs, golden):
+    """Config 2: all 1,830 consecutive pairs in one launch; every iteration's correspondence
+    vector, the iteration count, the pose and the error against the oracle; the pose also
+    against what the unmodified reference produced (golden fixture)."""
+    table = b200.ScanTable.from_list(cart_scans)
+    res = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5,
+                                 want_indices=True, want_src=True, want_history=True)
+    torch.cuda.synchronize()
+    for p, o in enumerate(oracle_pairs):
+        _check_pair(res, p, o, len(cart_scans[p + 1]))
+    pt = res.pose_total.cpu().numpy()
+    assert np.max(np.abs(_theta(pt) - golden["pair_theta_tot"])) < TIGHT_ROT
+    assert np.max(np.abs(pt[:, 4:6] - golden["pair_t_tot"])) < TIGHT_TRANS
+    pl = res.pose_last.cpu().numpy()
+    assert np.allclose(pl[:, :4].reshape(-1, 2, 2), golden["pair_R_last"], rtol=0, atol=1e-9)
+    assert np.allclose(pl[:, 4:6], golden["pair_t_last"], rtol=0, atol=1e-6)
+    # odometry chain == host prefix composition of oracle poses
+    chain = b200.chain_poses(res.pose_total)
+    R, t = np.eye(2), np.zeros(2)
+    for o in oracle_pairs:
+        t = R @ o.t_tot + t
+        R = R @ o.R_tot
+    assert np.allclose(chain[-1, :4].reshape(2, 2), R, atol=1e-7) and np.allclose(chain[-1, 4:], t, atol=1e-3)
+
+
+def test_float32_inputs_synthetic_rooms(b200):
+    """Config 3 shape (360 x 360, float32 tables), forced 30 iterations and tol 1e-5."""
+    count = 48
+    src, tgt = orc.synth_room_batch(0, count)
+    s = b200.ScanTable(torch.from_numpy(src).cuda())
+    t = b200.ScanTable(torch.from_numpy(tgt).cuda())
+    for tol in (-1.0, 1e-5):
+        res = b200.align_pairs(s, t, max_iterations=30, tolerance=tol, want_history=True, want_src=True)
+        for p in range(count):
+            o = orc.icp_extended(src[p], tgt[p], 30, tol)
+            if tol < 0:
+                assert o.iterations == 30
+            _check_pair(res, p, o, 360)
+
+
+def test_init_pose_and_gate(b200, cart_scans):
+    pairs = [2, 99, 350, 672, 1062, 1500]
+    A = [cart_scans[p + 1] for p in pairs]
+    B = [cart_scans[p] for p in pairs]
+    rng = np.random.default_rng(3)
+    poses = []
+    for _ in pairs:
+        th = rng.uniform(-0.05, 0.05)
+        poses.append([math.cos(th), -math.sin(th), math.sin(th), math.cos(th),
+                      rng.uniform(-50, 50), rng.uniform(-50, 50)])
+    init = torch.tensor(poses, dtype=torch.float64, device="cuda")
+    s, t = b200.ScanTable.from_list(A), b200.ScanTable.from_list(B)
+    for gate in (None, 150.0, 60.0, 1e-6):
+        res = b200.align_pairs(s, t, max_iterations=30, tolerance=1e-5, init_pose=init,
+                               max_corr_dist=gate, want_history=True, want_src=True)
+        for k in range(len(pairs)):
+            R0 = np.array(poses[k][:4]).reshape(2, 2)
+            t0 = np.array(poses[k][4:])
+            o = orc.icp_extended(A[k], B[k], 30, 1e-5, init_pose=(R0, t0), max_corr_dist=gate)
+            _check_pair(res, k, o, len(A[k]))
+            if o.iterations:
+                assert abs(float(res.rmse[k]) - o.rmse) < 1e-9 * max(1.0, o.rmse)
+                assert int(res.inliers[k]) == round(o.fitness * len(A[k]))
+            else:
+                assert math.isinf(float(res.error[k])) and int(res.inliers[k]) == 0
+
+
+def test_degenerate_pairs_do_not_fail_the_batch(b200, cart_scans):
+    A = [np.zeros((0, 2)), cart_scans[4], cart_scans[6], np.array([[10.0, 20.0]])]
+    B = [cart_scans[3], np.zeros((0, 2)), cart_scans[5], np.array([[11.0, 22.0]])]
+    s, t = b200.ScanTable.from_list(A), b200.ScanTable.from_list(B)
+    res = b200.align_pairs(s, t, max_iterations=30, tolerance=1e-5, want_src=True)
+    it = res.iterations.cpu().numpy()
+    err = res.error.cpu().numpy()
+    pt = res.pose_total.cpu().numpy()
+    assert it[0] == 0 and it[1] == 0 and np.isinf(err[0]) and np.isinf(err[1])
+    assert np.array_equal(pt[0], [1, 0, 0, 1, 0, 0]) and np.array_equal(pt[1], [1, 0, 0, 1, 0, 0])
+    o = orc.icp_extended(A[2], B[2], 30, 1e-5)
+    _check_pair(res, 2, o, len(A[2]), history=False)
+    # one point onto one point: H = 0, R = I, pure translation
+    o1 = orc.icp_extended(A[3], B[3], 30, 1e-5)
+    assert np.allclose(pt[3, 4:6], [1.0, 2.0], atol=1e-12) and it[3] == o1.iterations == 3
+    zero = b200.align_pairs(s, t, max_iterations=0, want_src=True)
+    assert np.all(zero.iterations.cpu().numpy() == 0)
+    assert np.allclose(zero.src_final[2, :len(A[2])].cpu().numpy(), A[2])
+
+
+def test_pairings_agree(b200, cart_scans):
+    rows = cart_scans[100:108]
+    table = b200.ScanTable.from_list(rows)
+    n = len(rows)
+    tri = b200.align_pairs(table, table, pairing="triangle", max_iterations=30, tolerance=1e-5)
+    count = n * (n - 1) // 2
+    assert tri.pose_total.shape[0] == count
+    ii, jj = [], []
+    for q in range(count):
+        i, j = b200.triangle_pair(q, n)
+        ii.append(i); jj.append(j)
+    sr = torch.tensor(jj, dtype=torch.int32, device="cuda")
+    tr = torch.tensor(ii, dtype=torch.int32, device="cuda")
+    exp = b200.align_pairs(table, table, pairing="explicit", src_row=sr, tgt_row=tr,
+                           max_iterations=30, tolerance=1e-5)
+    assert torch.equal(tri.pose_total, exp.pose_total) and torch.equal(tri.iterations, exp.iterations)
+    # a shard of the triangle starting mid-way
+    part = b200.align_pairs(table, table, pairing="triangle", first_pair=11, n_pairs=9,
+                            max_iterations=30, tolerance=1e-5)
+    assert torch.equal(part.pose_total, tri.pose_total[11:20])
+    for q in (0, 5, count - 1):
+        o = orc.icp_extended(rows[jj[q]], rows[ii[q]], 30, 1e-5)
+        _check_pair(tri, q, o, len(rows[jj[q]]), history=False)
+
+
+def test_full_size_batch_properties(b200):
+    """Config 3 at full size (65,536 x 360 x 360 x 30 forced iterations): determinism, batch-
+    position independence, sampled oracle parity."""
+    base = 64
+    src, tgt = orc.synth_room_batch(0, base)
+    reps = 65536 // base
+    S = torch.from_numpy(src).cuda().repeat(reps, 1, 1)
+    T = torch.from_numpy(tgt).cuda().repeat(reps, 1, 1)
+    s, t = b200.ScanTable(S), b200.ScanTable(T)
+    r1 = b200.align_pairs(s, t, max_iterations=30, tolerance=-1.0, want_indices=True)
+    r2 = b200.align_pairs(s, t, max_iterations=30, tolerance=-1.0, want_indices=True)
+    torch.cuda.synchronize()
+    assert torch.equal(r1.pose_total, r2.pose_total) and torch.equal(r1.indices, r2.indices)
+    assert torch.all(r1.iterations == 30)
+    tiled = r1.pose_total.reshape(reps, base, 6)
+    assert torch.equal(tiled, tiled[0:1].expand(reps, base, 6))          # same pair, same bits
+    for p in (0, 17, 63):
+        o = orc.icp_extended(src[p], tgt[p], 30, -1.0)
+        _check_pair(r1, 65536 - base + p, o, 360, history=False)
+
+
+def test_self_alignment_is_identity(b200, cart_scans):
+    table = b200.ScanTable.from_list(cart_scans[200:232])
+    res = b200.align_pairs(table, table, max_iterations=30, tolerance=1e-5)
+    pt = res.pose_total.cpu().numpy()
+    assert np.all(res.iterations.cpu().numpy() == 1)              # quirk Q3
+    assert np.allclose(pt[:, :4], [1, 0, 0, 1], atol=1e-15) and np.max(np.abs(pt[:, 4:])) < 1e-10
+    assert np.all(res.error.cpu().numpy() == 0.0)
+
+
+# ---------------------------------------------------------------------------------------
+# scan preparation (process.py:38-52) and the reference-shaped wrappers
+# ---------------------------------------------------------------------------------------
+def test_polar_to_cartesian_device(b200, raw_scans, cart_scans):
+    table = b200.scan_io.prepare_scans(raw_scans)
+    lens = table.lengths.cpu().numpy()
+    pts = table.points.cpu().numpy()
+    exact = total = 0
+    for k, c in enumerate(cart_scans):
+        assert lens[k] == len(c), f"scan {k + 1}"
+        got = pts[k, :len(c)]
+        # device sin/cos are <= 2 ulp, libm's are <= 1 ulp: coordinates agree to ~1e-12 mm
+        assert np.allclose(got, c, rtol=0, atol=1e-9)
+        exact += int(np.sum(got == c)); total += c.size
+    assert exact / total > 0.5
+
+
+def test_reference_shaped_wrappers(b200, cart_scans):
+    A, B = cart_scans[3], cart_scans[2]
+    d, i = b200.nearest_neighbors(A, B)
+    dr, ir = orc.nn_kdtree(A, B)
+    assert np.array_equal(i, ir) and np.allclose(d, dr, rtol=1e-14)
+    rmse, T = b200.registration_p2p(np.c_[A, np.zeros(len(A))], np.c_[B, np.zeros(len(B))],
+                                    threshold=200.0, trans_init=np.eye(4), max_iteration=50)
+    o = orc.icp_extended(A, B, 50, 1e-5, init_pose=(np.eye(2), np.zeros(2)), max_corr_dist=200.0)
+    assert abs(rmse - o.rmse) < 1e-9 and np.allclose(T[:2, :2], o.R_tot, atol=1e-9)
+    assert np.allclose(T[:2, 3], o.t_tot, atol=1e-6) and T.shape == (4, 4)
+    r, T = b200.registration_p2p(A[:5], B)                     # gicp_lidar.py:13-15 guard
+    assert math.isinf(r) and np.array_equal(T, np.eye(4))
+    with pytest.raises(ValueError):
+        b200.icp(np.zeros((0, 2)), B)
