@@ -69,7 +69,8 @@ class B200IcpError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library; ``B200ICP_LIB`` points at an alternative build (kernel A/B runs)."""
+    return os.environ.get("B200ICP_LIB") or _build.LIB_PATH
 
 
 def lib():

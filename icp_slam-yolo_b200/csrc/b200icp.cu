@@ -38,8 +38,14 @@ constexpr int kMaxWarps = 8;       // CTA size limit of the per-pair kernels
 constexpr int kMaxS = 4;           // source points per lane
 constexpr int kMaxSrcPitch = kMaxS * kMaxWarps * 32;   // 1024
 constexpr int kMaxTgtPitch = 4096;
-constexpr int kRedStride = 8;      // doubles per warp slot in the reduction scratch
+constexpr int kRedStride = 8;      // doubles per warp slot in the staging reductions
+constexpr int kRedStride2 = 12;    // doubles per warp slot in the per-iteration reduction
 constexpr unsigned kFull = 0xffffffffu;
+// CTAs of kMaxWarps warps that must fit one SM: caps registers per thread
+// (65536 / (256 * kMinBlocks)); typical CTAs have 4 warps, so twice as many are resident.
+#ifndef B200ICP_MIN_BLOCKS
+#define B200ICP_MIN_BLOCKS 2
+#endif
 
 thread_local char g_last_error[512] = "";
 
@@ -98,6 +104,7 @@ __device__ __forceinline__ double2 load_point(const void* base, int dtype, int64
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* scratch, int warp, int lane,
                                           int nwarps) {
+  constexpr int kStride = K <= kRedStride ? kRedStride : kRedStride2;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -105,50 +112,102 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* scratch, int w
   }
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) scratch[warp * kRedStride + k] = v[k];
+    for (int k = 0; k < K; ++k) scratch[warp * kStride + k] = v[k];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double acc = scratch[k];
-    for (int w = 1; w < nwarps; ++w) acc += scratch[w * kRedStride + k];
+    for (int w = 1; w < nwarps; ++w) acc += scratch[w * kStride + k];
     v[k] = acc;
   }
 }
 
 // ------------------------------------------------------------------------------------
-// target staging: float64 (x,y) + negated float32 SoA + pad; returns max |coordinate|
+// shared-memory tile of one target scan
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ float stage_targets(const void* tgt, int dtype, int64_t row_off, int m,
-                                               int mcap, double2* t64, float* ntx, float* nty,
-                                               float* wmax, int tid, int nthreads, int warp,
-                                               int lane, int nwarps) {
-  float amax = 0.f;
-  for (int j = tid; j < mcap; j += nthreads) {
+struct TargetTile {
+  double2* t64;    // [mcap] exact float64 points (sentinel = +inf beyond m)
+  float* fx;       // [mcap] centred float32 x   (direct form stores the NEGATED value)
+  float* fy;       // [mcap] centred float32 y
+  float* ft;       // [mcap] |centred point|^2 rounded once (expanded form only)
+  double* red;     // [2][kMaxWarps][kRedStride2] reduction scratch (double buffered)
+  float* wmax;     // [kMaxWarps]
+  double ox, oy;   // origin = target centroid; distances are translation invariant and
+                   // small centred magnitudes keep the FP32 guard band narrow
+  float tmax;      // max |centred target coordinate|
+  int m, mcap, ngroups;
+};
+
+__host__ __device__ inline size_t tile_bytes(int mcap) {
+  return (size_t)mcap * (sizeof(double2) + 3 * sizeof(float)) +
+         2 * kMaxWarps * kRedStride2 * sizeof(double) + kMaxWarps * sizeof(float);
+}
+
+__device__ __forceinline__ void carve_tile(unsigned char* smem, int mcap, TargetTile& t) {
+  t.t64 = reinterpret_cast<double2*>(smem);
+  t.fx = reinterpret_cast<float*>(t.t64 + mcap);
+  t.fy = t.fx + mcap;
+  t.ft = t.fy + mcap;
+  // mcap is a multiple of 8, so (16 + 12) * mcap keeps 8-byte alignment for the doubles
+  t.red = reinterpret_cast<double*>(t.ft + mcap);
+  t.wmax = reinterpret_cast<float*>(t.red + 2 * kMaxWarps * kRedStride2);
+  t.mcap = mcap;
+}
+
+// Stage the target scan: float64 copy, centroid, centred float32 SoA copies (+ |t|^2), pad.
+template <bool EXPANDED>
+__device__ __forceinline__ void stage_targets(const void* tgt, int dtype, int64_t row_off, int m,
+                                              TargetTile& t, int tid, int nthreads, int warp,
+                                              int lane, int nwarps) {
+  t.m = m;
+  t.ngroups = (m + kGroup - 1) / kGroup;
+  double sum[2] = {0.0, 0.0};
+  for (int j = tid; j < t.mcap; j += nthreads) {
+    double2 q = make_double2(CUDART_INF, CUDART_INF);      // sentinel: infinitely far
     if (j < m) {
-      const double2 q = load_point(tgt, dtype, row_off + j);
-      t64[j] = q;
-      const float fx = (float)q.x, fy = (float)q.y;
-      ntx[j] = -fx;
-      nty[j] = -fy;
-      amax = fmaxf(amax, fmaxf(fabsf(fx), fabsf(fy)));
-    } else {                       // sentinel targets: infinitely far, never win
-      t64[j] = make_double2(CUDART_INF, CUDART_INF);
-      ntx[j] = CUDART_INF_F;
-      nty[j] = CUDART_INF_F;
+      q = load_point(tgt, dtype, row_off + j);
+      sum[0] += q.x; sum[1] += q.y;
+    }
+    t.t64[j] = q;
+  }
+  block_sum<2>(sum, t.red, warp, lane, nwarps);             // syncs: t64 is visible after this
+  t.ox = sum[0] / (double)m;
+  t.oy = sum[1] / (double)m;
+  float amax = 0.f;
+  for (int j = tid; j < t.mcap; j += nthreads) {
+    if (j < m) {
+      const double2 q = t.t64[j];
+      const float cx = (float)(q.x - t.ox), cy = (float)(q.y - t.oy);
+      amax = fmaxf(amax, fmaxf(fabsf(cx), fabsf(cy)));
+      if (EXPANDED) {
+        t.fx[j] = cx; t.fy[j] = cy;
+        t.ft[j] = (float)((double)cx * (double)cx + (double)cy * (double)cy);
+      } else {
+        t.fx[j] = -cx; t.fy[j] = -cy;
+      }
+    } else if (EXPANDED) {
+      t.fx[j] = 0.f; t.fy[j] = 0.f; t.ft[j] = CUDART_INF_F;
+    } else {
+      t.fx[j] = CUDART_INF_F; t.fy[j] = CUDART_INF_F;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
-  if (lane == 0) wmax[warp] = amax;
+  if (lane == 0) t.wmax[warp] = amax;
   __syncthreads();
-  float r = wmax[0];
-  for (int w = 1; w < nwarps; ++w) r = fmaxf(r, wmax[w]);
-  return r;
+  float r = t.wmax[0];
+  for (int w = 1; w < nwarps; ++w) r = fmaxf(r, t.wmax[w]);
+  t.tmax = r;
 }
 
 // ------------------------------------------------------------------------------------
-// candidate search (FP32, packed): per source the best group, its min, runner-up group min
+// candidate search (FP32): per source the best group of 8 targets, its minimum and the
+// runner-up group minimum.  Two arithmetic forms of the same brute-force sweep:
+//   EXPANDED: e_j = |t_j|^2 - 2 s.t_j  (= d^2 - |s|^2)    2 FFMA + 1 FMNMX per pair
+//   direct  : d_j = (sx - tx_j)^2 + (sy - ty_j)^2            2 FADD + FMUL + FFMA + FMNMX
+// The expanded form is ~1.6x cheaper in issue slots; its larger rounding error only widens
+// the guard band of nn_resolve, never the result.
 // ------------------------------------------------------------------------------------
 template <int S>
 struct Candidates {
@@ -158,48 +217,65 @@ struct Candidates {
 };
 
 template <int S>
-__device__ __forceinline__ void nn_candidates(const float* __restrict__ ntx,
-                                              const float* __restrict__ nty, int ngroups,
-                                              const float (&sx)[S], const float (&sy)[S],
-                                              Candidates<S>& c) {
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(ntx);
-  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(nty);
-  float2 sxx[S], syy[S];
+__device__ __forceinline__ void track(Candidates<S>& c, int k, float m, int g) {
+  const float old = c.best[k];
+  c.second[k] = fminf(c.second[k], fmaxf(old, m));
+  c.group[k] = (m < old) ? g : c.group[k];
+  c.best[k] = fminf(old, m);
+}
+
+template <int S, bool EXPANDED>
+__device__ __forceinline__ void nn_candidates(const TargetTile& t, const float (&sx)[S],
+                                              const float (&sy)[S], Candidates<S>& c) {
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
+  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
+  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(t.ft);
+  float a[S], b[S];
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    float vx = sx[k], vy = sy[k];
+    float vx = EXPANDED ? -2.0f * sx[k] : sx[k];
+    float vy = EXPANDED ? -2.0f * sy[k] : sy[k];
     // opaque copies: stops ptxas from re-converting the float64 state inside the loop
     asm volatile("" : "+f"(vx), "+f"(vy));
-    sxx[k] = make_float2(vx, vx);
-    syy[k] = make_float2(vy, vy);
+    a[k] = vx; b[k] = vy;
     c.best[k] = CUDART_INF_F;
     c.second[k] = CUDART_INF_F;
     c.group[k] = 0;
   }
+  const int ngroups = t.ngroups;
 #pragma unroll 1
   for (int g = 0; g < ngroups; ++g) {
     const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
     const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
+    if (EXPANDED) {
+      const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
 #pragma unroll
-    for (int k = 0; k < S; ++k) {
-      const float2 dx0 = __fadd2_rn(sxx[k], make_float2(xa.x, xa.y));
-      const float2 dx1 = __fadd2_rn(sxx[k], make_float2(xa.z, xa.w));
-      const float2 dx2 = __fadd2_rn(sxx[k], make_float2(xb.x, xb.y));
-      const float2 dx3 = __fadd2_rn(sxx[k], make_float2(xb.z, xb.w));
-      const float2 dy0 = __fadd2_rn(syy[k], make_float2(ya.x, ya.y));
-      const float2 dy1 = __fadd2_rn(syy[k], make_float2(ya.z, ya.w));
-      const float2 dy2 = __fadd2_rn(syy[k], make_float2(yb.x, yb.y));
-      const float2 dy3 = __fadd2_rn(syy[k], make_float2(yb.z, yb.w));
-      const float2 d0 = __ffma2_rn(dy0, dy0, __fmul2_rn(dx0, dx0));
-      const float2 d1 = __ffma2_rn(dy1, dy1, __fmul2_rn(dx1, dx1));
-      const float2 d2 = __ffma2_rn(dy2, dy2, __fmul2_rn(dx2, dx2));
-      const float2 d3 = __ffma2_rn(dy3, dy3, __fmul2_rn(dx3, dx3));
-      const float m = fminf(fminf(fminf(d0.x, d0.y), fminf(d1.x, d1.y)),
-                            fminf(fminf(d2.x, d2.y), fminf(d3.x, d3.y)));
-      const float old = c.best[k];
-      c.second[k] = fminf(c.second[k], fmaxf(old, m));
-      c.group[k] = (m < old) ? g : c.group[k];
-      c.best[k] = fminf(old, m);
+      for (int k = 0; k < S; ++k) {
+        // packed FP32x2: two targets per FFMA2 issue slot (the loop is issue/ALU bound,
+        // not FMA-pipe bound: profiles/r1_ubench_issue_rates.txt)
+        const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
+        const float2 e01 = __ffma2_rn(ak, make_float2(xa.x, xa.y), __ffma2_rn(bk, make_float2(ya.x, ya.y), make_float2(qa.x, qa.y)));
+        const float2 e23 = __ffma2_rn(ak, make_float2(xa.z, xa.w), __ffma2_rn(bk, make_float2(ya.z, ya.w), make_float2(qa.z, qa.w)));
+        const float2 e45 = __ffma2_rn(ak, make_float2(xb.x, xb.y), __ffma2_rn(bk, make_float2(yb.x, yb.y), make_float2(qb.x, qb.y)));
+        const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
+        const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
+                              fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
+        track<S>(c, k, m, g);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const float u0 = a[k] + xa.x, v0 = b[k] + ya.x, u1 = a[k] + xa.y, v1 = b[k] + ya.y;
+        const float u2 = a[k] + xa.z, v2 = b[k] + ya.z, u3 = a[k] + xa.w, v3 = b[k] + ya.w;
+        const float u4 = a[k] + xb.x, v4 = b[k] + yb.x, u5 = a[k] + xb.y, v5 = b[k] + yb.y;
+        const float u6 = a[k] + xb.z, v6 = b[k] + yb.z, u7 = a[k] + xb.w, v7 = b[k] + yb.w;
+        const float d0 = fmaf(v0, v0, u0 * u0), d1 = fmaf(v1, v1, u1 * u1);
+        const float d2 = fmaf(v2, v2, u2 * u2), d3 = fmaf(v3, v3, u3 * u3);
+        const float d4 = fmaf(v4, v4, u4 * u4), d5 = fmaf(v5, v5, u5 * u5);
+        const float d6 = fmaf(v6, v6, u6 * u6), d7 = fmaf(v7, v7, u7 * u7);
+        const float m = fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(fminf(d4, d5), fminf(d6, d7)));
+        track<S>(c, k, m, g);
+      }
     }
   }
 }
@@ -211,26 +287,44 @@ __device__ __forceinline__ double dist2_f64(double sx, double sy, double2 t) {
   return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
+// How far above the FP32 best another group's minimum may lie and still hide the true
+// (float64) nearest neighbour.  u = 2^-24.  cs = max |centred source coordinate| (FP32).
+//   direct  : sqrt(d32) is within 2.9*eta of the true distance, eta = (cs + tmax) * 2u
+//             -> compare distances:  thr = (sqrt(best)(1 + 2^-20) + 4*eta)^2 (1 + 2^-22)
+//   expanded: |e32 - e_exact| <= 6u*tmax*(cs + tmax) per value (tt rounding + two FMAs) and
+//             the FP32-rounded points sit within rho = 2.83u*max(cs,tmax) of the true
+//             ones -> margin = 2*8u*tmax*(cs+tmax) + 4*dB*rho + 2*rho^2 on (second - best),
+//             dB an upper bound of the best distance.            (Derivations: DESIGN.md)
+template <bool EXPANDED>
+__device__ __forceinline__ bool is_ambiguous(float best, float second, float scx, float scy,
+                                             float tmax) {
+  const float cs = fmaxf(fabsf(scx), fabsf(scy));
+  if (EXPANDED) {
+    const float E2 = 9.5367432e-7f * tmax * (cs + tmax);                    // 2 * 8u * ...
+    const float rho = 1.6868114e-7f * fmaxf(cs, tmax);                      // 2.83 u
+    const float ss = fmaf(scx, scx, scy * scy);
+    const float dB = sqrtf(fmaxf(best + ss, 0.f) + E2) * 1.000001f;
+    const float margin = (E2 + 4.f * dB * rho + 2.f * rho * rho) * 1.000001f;
+    return (second - best) <= margin;        // near-equal floats subtract exactly
+  }
+  const float guard = (cs + tmax) * 4.76837158e-7f;                         // 4*eta = 2^-21 (..)
+  const float r = sqrtf(best) * 1.00000095f + guard;
+  return second <= r * r * 1.00000024f;
+}
+
 // Re-decide every correspondence in float64.  Must be called by all lanes of the warp.
-//   valid[k]  : lane owns a real source point in slot k
-//   gscale    : 2^-21 * (max |target coord|) pre-added per source below
-template <int S>
-__device__ __forceinline__ void nn_resolve(const double2* __restrict__ t64, int m,
-                                           const Candidates<S>& c, const double (&sx)[S],
-                                           const double (&sy)[S], const bool (&valid)[S],
-                                           float tmax, int lane, int (&idx)[S], double (&d2)[S]) {
+template <int S, bool EXPANDED>
+__device__ __forceinline__ void nn_resolve(const TargetTile& t, const Candidates<S>& c,
+                                           const double (&sx)[S], const double (&sy)[S],
+                                           const float (&fx)[S], const float (&fy)[S],
+                                           const bool (&valid)[S], int lane, int (&idx)[S],
+                                           double (&d2)[S]) {
+  const double2* __restrict__ t64 = t.t64;
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    // FP32 guard band: sqrt(d32) is within ~2.9*eta of the true distance for every target,
-    // eta = (|s|+|t|)max * 2^-23; anything with sqrt(d32) <= sqrt(best)(1+2^-20) + 4*eta
-    // could be the true nearest neighbour.  (Derivation in DESIGN.md.)
-    const float smag = fmaxf(fabsf((float)sx[k]), fabsf((float)sy[k]));
-    const float guard = (smag + tmax) * 4.76837158e-7f;                 // 2^-21
-    const float r = sqrtf(c.best[k]) * 1.00000095f + guard;             // 1 + 2^-20
-    const float thr = r * r * 1.00000024f;
-    const bool ambiguous = valid[k] && (c.second[k] <= thr);
-
+    const bool ambiguous = valid[k] && is_ambiguous<EXPANDED>(c.best[k], c.second[k], fx[k], fy[k], t.tmax);
     // fast path: the winner is inside the best group; rescan its 8 targets exactly
+    // (ascending index, strict <: lowest index wins exact ties)
     double bd = CUDART_INF;
     int bj = c.group[k] * kGroup;
     if (valid[k]) {
@@ -250,7 +344,7 @@ __device__ __forceinline__ void nn_resolve(const double2* __restrict__ t64, int 
       const double qy = __shfl_sync(kFull, sy[k], owner);
       double ld = CUDART_INF;
       int lj = 0x7fffffff;
-      for (int j = lane; j < m; j += 32) {
+      for (int j = lane; j < t.m; j += 32) {
         const double d = dist2_f64(qx, qy, t64[j]);
         if (d < ld) { ld = d; lj = j; }
       }
@@ -267,17 +361,30 @@ __device__ __forceinline__ void nn_resolve(const double2* __restrict__ t64, int 
   }
 }
 
+// One full search for the S source points a lane owns (float64 in, exact answer out).
+template <int S, bool EXPANDED>
+__device__ __forceinline__ void nn_search(const TargetTile& t, const double (&sx)[S],
+                                          const double (&sy)[S], const bool (&valid)[S], int lane,
+                                          int (&idx)[S], double (&d2)[S]) {
+  float fx[S], fy[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    fx[k] = (float)(sx[k] - t.ox);
+    fy[k] = (float)(sy[k] - t.oy);
+  }
+  Candidates<S> c;
+  nn_candidates<S, EXPANDED>(t, fx, fy, c);
+  nn_resolve<S, EXPANDED>(t, c, sx, sy, fx, fy, valid, lane, idx, d2);
+}
+
 // ------------------------------------------------------------------------------------
 // kernel: nearest-neighbour search only (icp.py:37-38)
 // ------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(kMaxWarps * 32) nn_pair_kernel(const KernelArgs a) {
+template <int S, bool EXPANDED>
+__global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) nn_pair_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int mcap = a.mcap;
-  double2* t64 = reinterpret_cast<double2*>(smem_raw);
-  float* ntx = reinterpret_cast<float*>(t64 + mcap);
-  float* nty = ntx + mcap;
-  float* wmax = nty + mcap;
+  TargetTile t;
+  carve_tile(smem_raw, a.mcap, t);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -298,25 +405,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32) nn_pair_kernel(const KernelArg
     }
     return;
   }
-  const float tmax = stage_targets(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, mcap, t64, ntx,
-                                   nty, wmax, tid, nthreads, warp, lane, nwarps);
+  stage_targets<EXPANDED>(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, t, tid, nthreads, warp,
+                          lane, nwarps);
   double sx[S], sy[S];
-  float fx[S], fy[S];
   bool valid[S];
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     const int i = tid + k * nthreads;
     valid[k] = i < n;
-    double2 q = make_double2(0.0, 0.0);
+    double2 q = make_double2(t.ox, t.oy);
     if (valid[k]) q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
     sx[k] = q.x; sy[k] = q.y;
-    fx[k] = (float)q.x; fy[k] = (float)q.y;
   }
-  Candidates<S> c;
-  nn_candidates<S>(ntx, nty, (m + kGroup - 1) / kGroup, fx, fy, c);
   int idx[S];
   double d2[S];
-  nn_resolve<S>(t64, m, c, sx, sy, valid, tmax, lane, idx, d2);
+  nn_search<S, EXPANDED>(t, sx, sy, valid, lane, idx, d2);
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     const int i = tid + k * nthreads;
@@ -330,15 +433,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) nn_pair_kernel(const KernelArg
 // ------------------------------------------------------------------------------------
 // kernel: the whole ICP loop for one pair (icp.py:28-53)
 // ------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelArgs a) {
+template <int S, bool EXPANDED>
+__global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) icp_align_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int mcap = a.mcap;
-  double2* t64 = reinterpret_cast<double2*>(smem_raw);
-  float* ntx = reinterpret_cast<float*>(t64 + mcap);
-  float* nty = ntx + mcap;
-  double* red = reinterpret_cast<double*>(nty + mcap);          // [2][kMaxWarps][kRedStride]
-  float* wmax = reinterpret_cast<float*>(red + 2 * kMaxWarps * kRedStride);
+  TargetTile t;
+  carve_tile(smem_raw, a.mcap, t);
+  double* red = t.red;
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -359,7 +459,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
     R00 = ip[0]; R01 = ip[1]; R10 = ip[2]; R11 = ip[3]; T0 = ip[4]; T1 = ip[5];
   }
   double c_last = 1.0, s_last = 0.0, t0_last = 0.0, t1_last = 0.0;   // last increment
-  double err = CUDART_INF, rmse = CUDART_INF;
+  double err = CUDART_INF, mean_d2 = CUDART_INF;
   int iters = 0, inl = 0;
 
   double sx[S], sy[S];
@@ -370,8 +470,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
 
   const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
   if (ran) {
-    const float tmax = stage_targets(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, mcap, t64,
-                                     ntx, nty, wmax, tid, nthreads, warp, lane, nwarps);
+    stage_targets<EXPANDED>(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, t, tid, nthreads,
+                            warp, lane, nwarps);
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const int i = tid + k * nthreads;
@@ -386,42 +486,39 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
         }
       }
     }
-    const int ngroups = (m + kGroup - 1) / kGroup;
     const double gate = op.max_corr_dist;
     const bool use_gate = a.use_gate != 0;
+    const double inv_n = 1.0 / (double)n;
     double prev_error = 0.0;                                   // icp.py:33
 
     for (int it = 0; it < op.max_iterations; ++it) {           // icp.py:35
       // ---- correspondence search (icp.py:37-38)
-      float fx[S], fy[S];
-#pragma unroll
-      for (int k = 0; k < S; ++k) { fx[k] = (float)sx[k]; fy[k] = (float)sy[k]; }
-      Candidates<S> c;
-      nn_candidates<S>(ntx, nty, ngroups, fx, fy, c);
       double d2[S];
-      nn_resolve<S>(t64, m, c, sx, sy, valid, tmax, lane, idx, d2);
-      // ---- gather matches (icp.py:39), gate, first reduction: centroids + distance sums
-      double bx[S], by[S];
-      bool use[S];
-      double r1[7] = {0, 0, 0, 0, 0, 0, 0};   // sum ax, ay, bx, by, dist, dist^2, count
+      nn_search<S, EXPANDED>(t, sx, sy, valid, lane, idx, d2);
+      // ---- gather matches (icp.py:39), gate, ONE reduction of centred sums.
+      // Coordinates are taken relative to the tile origin (the target centroid), so the
+      // single-pass covariance  H = sum a'b'^T - (sum a')(sum b')^T / n  (icp.py:10-16) loses
+      // nothing to cancellation: |centroid offsets| << point spread.
+      double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int k = 0; k < S; ++k) {
-        bx[k] = 0.0; by[k] = 0.0; use[k] = false;
         if (valid[k]) {
           const double dist = sqrt(d2[k]);
-          use[k] = !use_gate || dist < gate;
-          if (use[k]) {
-            const double2 b = t64[idx[k]];
-            bx[k] = b.x; by[k] = b.y;
-            r1[0] += sx[k]; r1[1] += sy[k]; r1[2] += b.x; r1[3] += b.y;
-            r1[4] += dist; r1[5] += d2[k]; r1[6] += 1.0;
+          if (!use_gate || dist < gate) {
+            const double2 b = t.t64[idx[k]];
+            const double ax = sx[k] - t.ox, ay = sy[k] - t.oy;
+            const double qx = b.x - t.ox, qy = b.y - t.oy;
+            r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
+            r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
+            r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
+            r[8] += dist; r[9] += d2[k]; r[10] += 1.0;
           }
         }
       }
-      block_sum<7>(r1, red, warp, lane, nwarps);
-      const double cnt = r1[6];
+      block_sum<11>(r, red + (it & 1) * kMaxWarps * kRedStride2, warp, lane, nwarps);
+      const double cnt = r[10];
       if (cnt < 0.5) {            // every correspondence gated out: stop, search not counted
-        err = CUDART_INF; rmse = CUDART_INF; inl = 0;
+        err = CUDART_INF; mean_d2 = CUDART_INF; inl = 0;
         break;
       }
       if (out.index_history) {
@@ -432,28 +529,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
           if (i < pr.src_pitch) h[i] = valid[k] ? idx[k] : -1;
         }
       }
-      const double inv = 1.0 / cnt;
-      const double cax = r1[0] * inv, cay = r1[1] * inv;       // icp.py:10
-      const double cbx = r1[2] * inv, cby = r1[3] * inv;       // icp.py:11
-      const double mean_error = r1[4] * inv;                   // icp.py:48
-      // ---- second reduction: centred 2x2 cross-covariance H = AA^T BB (icp.py:13-16)
-      double r2[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        if (use[k]) {
-          const double ax = sx[k] - cax, ay = sy[k] - cay;
-          const double qx = bx[k] - cbx, qy = by[k] - cby;
-          r2[0] += ax * qx; r2[1] += ax * qy; r2[2] += ay * qx; r2[3] += ay * qy;
-        }
-      }
-      block_sum<4>(r2, red + kMaxWarps * kRedStride, warp, lane, nwarps);
+      const double inv = use_gate ? 1.0 / cnt : inv_n;
+      const double max_ = r[0] * inv, may_ = r[1] * inv;        // centroids rel. origin (icp.py:10-11)
+      const double mbx = r[2] * inv, mby = r[3] * inv;
+      const double mean_error = r[8] * inv;                     // icp.py:48
       // ---- closed-form 2D Kabsch: the proper rotation the SVD route (icp.py:17-23) returns
-      const double num = r2[1] - r2[2], den = r2[0] + r2[3];
-      const double hyp = sqrt(num * num + den * den);
+      const double h00 = fma(-r[0], mbx, r[4]), h01 = fma(-r[0], mby, r[5]);
+      const double h10 = fma(-r[1], mbx, r[6]), h11 = fma(-r[1], mby, r[7]);
+      const double num = h01 - h10, den = h00 + h11;
+      const double h2 = fma(num, num, den * den);
       double cs = 1.0, sn = 0.0;
-      if (hyp > 0.0) { cs = den / hyp; sn = num / hyp; }
-      const double tx = cbx - (cs * cax - sn * cay);           // icp.py:25
-      const double ty = cby - (sn * cax + cs * cay);
+      if (h2 > 0.0) {
+        const double rh = rsqrt(h2);
+        cs = den * rh; sn = num * rh;
+      }
+      const double cax = t.ox + max_, cay = t.oy + may_;
+      const double tx = (t.ox + mbx) - (cs * cax - sn * cay);   // icp.py:25
+      const double ty = (t.oy + mby) - (sn * cax + cs * cay);
       // ---- apply (icp.py:45) and compose the cumulative pose
 #pragma unroll
       for (int k = 0; k < S; ++k) {
@@ -470,7 +562,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
         R00 = n00; R01 = n01; R10 = n10; R11 = n11; T0 = nt0; T1 = nt1;
       }
       c_last = cs; s_last = sn; t0_last = tx; t1_last = ty;
-      err = mean_error; rmse = sqrt(r1[5] * inv); inl = (int)(cnt + 0.5);
+      err = mean_error; mean_d2 = r[9] * inv; inl = (int)(cnt + 0.5);
       iters = it + 1;
       // ---- convergence (icp.py:49-51); identical in every thread
       if (fabs(prev_error - mean_error) < op.tolerance) break;
@@ -487,7 +579,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) icp_align_kernel(const KernelA
       pl[4] = t0_last; pl[5] = t1_last;
     }
     out.error[p] = err;
-    if (out.rmse) out.rmse[p] = rmse;
+    if (out.rmse) out.rmse[p] = sqrt(mean_d2);
     if (out.inliers) out.inliers[p] = inl;
     out.iterations[p] = iters;
   }
@@ -588,6 +680,7 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* sink, int inner_
 // host side
 // ------------------------------------------------------------------------------------
 struct LaunchShape {
+  bool expanded;   // search arithmetic: |t|^2 - 2 s.t (default) or direct differences
   int S;
   int warps;
   size_t smem;
@@ -613,8 +706,9 @@ bool pick_shape(const b200icp_problem* pr, bool align, LaunchShape& ls) {
   ls.S = S;
   ls.warps = warps;
   ls.mcap = (pr->tgt_pitch + kGroup - 1) / kGroup * kGroup;
-  ls.smem = (size_t)ls.mcap * (sizeof(double2) + 2 * sizeof(float)) +
-            (align ? 2 * kMaxWarps * kRedStride * sizeof(double) : 0) + kMaxWarps * sizeof(float);
+  (void)align;
+  ls.smem = tile_bytes(ls.mcap);
+  ls.expanded = env_int("B200ICP_SEARCH_DIRECT", 0) == 0;
   return true;
 }
 
@@ -700,12 +794,18 @@ int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs, int32_t* idx_
   args.n_pairs = n_pairs;
   args.mcap = ls.mcap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (ls.S) {
-    case 1: return launch_pairs(nn_pair_kernel<1>, ls, args, st);
-    case 2: return launch_pairs(nn_pair_kernel<2>, ls, args, st);
-    case 3: return launch_pairs(nn_pair_kernel<3>, ls, args, st);
-    default: return launch_pairs(nn_pair_kernel<4>, ls, args, st);
+#define B200ICP_DISPATCH(KERNEL)                                                        \
+  switch (ls.S * 2 + (ls.expanded ? 1 : 0)) {                                          \
+    case 2: return launch_pairs(KERNEL<1, false>, ls, args, st);                       \
+    case 3: return launch_pairs(KERNEL<1, true>, ls, args, st);                        \
+    case 4: return launch_pairs(KERNEL<2, false>, ls, args, st);                       \
+    case 5: return launch_pairs(KERNEL<2, true>, ls, args, st);                        \
+    case 6: return launch_pairs(KERNEL<3, false>, ls, args, st);                       \
+    case 7: return launch_pairs(KERNEL<3, true>, ls, args, st);                        \
+    case 8: return launch_pairs(KERNEL<4, false>, ls, args, st);                       \
+    default: return launch_pairs(KERNEL<4, true>, ls, args, st);                       \
   }
+  B200ICP_DISPATCH(nn_pair_kernel)
 }
 
 int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200icp_options* opt,
@@ -730,12 +830,7 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   args.mcap = ls.mcap;
   args.use_gate = (opt->max_corr_dist > 0.0 && std::isfinite(opt->max_corr_dist)) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (ls.S) {
-    case 1: return launch_pairs(icp_align_kernel<1>, ls, args, st);
-    case 2: return launch_pairs(icp_align_kernel<2>, ls, args, st);
-    case 3: return launch_pairs(icp_align_kernel<3>, ls, args, st);
-    default: return launch_pairs(icp_align_kernel<4>, ls, args, st);
-  }
+  B200ICP_DISPATCH(icp_align_kernel)
 }
 
 int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_t n_scans,
