@@ -46,6 +46,11 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef B200ICP_MIN_BLOCKS
 #define B200ICP_MIN_BLOCKS 2
 #endif
+// resident one-warp CTAs per SM the warp-per-pair kernel is compiled for (register cap
+// 65536 / (32 * this), rounded down to the allocation granule)
+#ifndef B200ICP_WARP_MIN_BLOCKS
+#define B200ICP_WARP_MIN_BLOCKS 16
+#endif
 
 thread_local char g_last_error[512] = "";
 
@@ -61,6 +66,7 @@ struct KernelArgs {
   double* nn_dist2;     // nn kernel only
   int64_t n_pairs;
   int32_t mcap;         // tgt_pitch rounded up to kGroup
+  int32_t ncap;         // warp kernel: src_pitch rounded up to 32 * SC
   int32_t use_gate;
 };
 
@@ -607,6 +613,375 @@ __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) icp_align_
 }
 
 // ------------------------------------------------------------------------------------
+// kernel: the whole ICP loop, ONE WARP PER PAIR (icp.py:28-53)
+//
+// The per-iteration work outside the candidate sweep (exact re-decision, distance, sums,
+// pose solve) is what limits the block-per-pair kernel above: with 4 warps per pair every
+// warp repeats the pose solve, the reductions cross shared memory and two barriers, and the
+// float64 rescans run at FP64-pipe rate.  Here a single warp owns the pair:
+//   * no block barrier anywhere; reductions are warp shuffles only; the pose is solved once;
+//   * each lane sweeps SC source points per pass (all 360 points of a scan in one pass at
+//     SC = 12), so one set of target LDS feeds 8*SC pair-evals;
+//   * shared memory per warp holds only the centred float32 SoA target tile and the float64
+//     source state; the float64 targets stay in global memory (L1/L2) and are touched once
+//     per source per iteration (the matched point), because the in-group decision is made in
+//     FP32 direct-difference form first (error ~1e-3 mm) and only near-ties fall back to the
+//     warp-cooperative float64 scan.
+// ------------------------------------------------------------------------------------
+struct WarpTile {
+  const void* tgt;      // global target table
+  int64_t row_off;      // first point of this pair's target row
+  int dtype;
+  float* fx;            // [mcap] centred float32 x
+  float* fy;            // [mcap]
+  float* ft;            // [mcap] |centred|^2, +inf sentinels
+  double2* src;         // [ncap] float64 source state
+  double ox, oy;
+  float tmax;
+  int m, mcap, ngroups;
+};
+
+__host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap) {
+  return (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + 160 /* WarpCtx */;
+}
+
+__device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
+  double sx = 0.0, sy = 0.0;
+  for (int j = lane; j < t.m; j += 32) {
+    const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
+    sx += q.x; sy += q.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(kFull, sx, o);
+    sy += __shfl_xor_sync(kFull, sy, o);
+  }
+  t.ox = sx / (double)t.m;
+  t.oy = sy / (double)t.m;
+  float amax = 0.f;
+  for (int j = lane; j < t.mcap; j += 32) {
+    float cx = 0.f, cy = 0.f, tt = CUDART_INF_F;
+    if (j < t.m) {
+      const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
+      cx = (float)(q.x - t.ox); cy = (float)(q.y - t.oy);
+      tt = (float)((double)cx * (double)cx + (double)cy * (double)cy);
+      amax = fmaxf(amax, fmaxf(fabsf(cx), fabsf(cy)));
+    }
+    t.fx[j] = cx; t.fy[j] = cy; t.ft[j] = tt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
+  t.tmax = amax;
+  __syncwarp();
+}
+
+// Candidate sweep over the warp tile (expanded form, packed FFMA2); same contract as
+// nn_candidates<S, true>.
+template <int S>
+__device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (&sx)[S],
+                                                const float (&sy)[S], Candidates<S>& c) {
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
+  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
+  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(t.ft);
+  float a[S], b[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    float vx = -2.0f * sx[k], vy = -2.0f * sy[k];
+    asm volatile("" : "+f"(vx), "+f"(vy));
+    a[k] = vx; b[k] = vy;
+    c.best[k] = CUDART_INF_F; c.second[k] = CUDART_INF_F; c.group[k] = 0;
+  }
+  const int ngroups = t.ngroups;
+#pragma unroll 1
+  for (int g = 0; g < ngroups; ++g) {
+    const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
+    const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
+    const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
+      const float2 e01 = __ffma2_rn(ak, make_float2(xa.x, xa.y), __ffma2_rn(bk, make_float2(ya.x, ya.y), make_float2(qa.x, qa.y)));
+      const float2 e23 = __ffma2_rn(ak, make_float2(xa.z, xa.w), __ffma2_rn(bk, make_float2(ya.z, ya.w), make_float2(qa.z, qa.w)));
+      const float2 e45 = __ffma2_rn(ak, make_float2(xb.x, xb.y), __ffma2_rn(bk, make_float2(yb.x, yb.y), make_float2(qb.x, qb.y)));
+      const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
+      const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
+                            fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
+      track<S>(c, k, m, g);
+    }
+  }
+}
+
+// Inside the best group: FP32 direct-difference distances of its 8 targets, the 3-bit slot
+// packed into the low mantissa bits (relative perturbation <= 2^-20, inside the guard), so
+// the argmin and the runner-up are plain min/max chains.  Returns the winning slot and
+// whether a runner-up lies inside the guard band.
+__device__ __forceinline__ int in_group_argmin(const WarpTile& t, int g, float fx, float fy,
+                                               bool& near_tie) {
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
+  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
+  const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
+  const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
+  const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+  const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+  const float* tt = t.ft + g * kGroup;
+  unsigned best = 0x7f800000u, second = 0x7f800000u;       // +inf as ordered bit patterns
+#pragma unroll
+  for (int u = 0; u < kGroup; ++u) {
+    const float dx = fx - xs[u], dy = fy - ys[u];
+    float d = fmaf(dy, dy, dx * dx);
+    if (u > 0 && tt[u] == CUDART_INF_F) d = CUDART_INF_F;   // sentinel slots never win
+    const unsigned key = (__float_as_uint(d) & ~7u) | (unsigned)u;   // d >= 0: bits are ordered
+    second = min(second, max(best, key));
+    best = min(best, key);
+  }
+  const float bd = __uint_as_float(best & ~7u), sd = __uint_as_float(second & ~7u);
+  const float cs = fmaxf(fabsf(fx), fabsf(fy));
+  const float guard = (cs + t.tmax) * 4.76837158e-7f;                // 2^-21 (cs + tmax)
+  const float r = sqrtf(bd) * 1.000004f + guard;
+  near_tie = sd <= r * r * 1.000001f;
+  return (int)(best & 7u);
+}
+
+// Per-pair state that is touched once per iteration lives in shared memory, not registers:
+// the sweep needs ~5 registers per source point and every long-lived double evicted from the
+// register file is one more independent FFMA2/FMNMX chain the scheduler can keep in flight.
+struct WarpCtx {
+  double R[4], T[2];          // cumulative pose, src = R A + T
+  double last[4];             // last increment: cos, sin, tx, ty
+  double err, mean_d2, prev_error;
+  double inv_n;
+  int iters, inl;
+};
+
+template <int SC>
+__global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int64_t p = blockIdx.x;
+  const b200icp_problem& pr = a.prob;
+  const b200icp_options& op = a.opt;
+  const b200icp_outputs& out = a.out;
+
+  int64_t srow, trow;
+  resolve_rows(pr, p, srow, trow);
+  const int n = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
+  const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
+
+  WarpTile t;
+  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
+  t.mcap = a.mcap; t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
+  t.fx = reinterpret_cast<float*>(smem_raw);
+  t.fy = t.fx + a.mcap;
+  t.ft = t.fy + a.mcap;
+  t.src = reinterpret_cast<double2*>(t.ft + a.mcap);       // 12*mcap bytes, mcap % 8 == 0
+  WarpCtx* ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
+
+  const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
+  if (lane == 0) {
+    double R00 = 1.0, R01 = 0.0, R10 = 0.0, R11 = 1.0, T0 = 0.0, T1 = 0.0;
+    if (op.init_pose) {
+      const double* ip = op.init_pose + p * 6;
+      R00 = ip[0]; R01 = ip[1]; R10 = ip[2]; R11 = ip[3]; T0 = ip[4]; T1 = ip[5];
+    }
+    ctx->R[0] = R00; ctx->R[1] = R01; ctx->R[2] = R10; ctx->R[3] = R11;
+    ctx->T[0] = T0; ctx->T[1] = T1;
+    ctx->last[0] = 1.0; ctx->last[1] = 0.0; ctx->last[2] = 0.0; ctx->last[3] = 0.0;
+    ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->prev_error = 0.0;   // icp.py:33
+    ctx->inv_n = n > 0 ? 1.0 / (double)n : 0.0;
+    ctx->iters = 0; ctx->inl = 0;
+  }
+  __syncwarp();
+  int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
+
+  if (ran) {
+    warp_stage_targets(t, lane);
+    for (int i = lane; i < a.ncap; i += 32) {
+      double2 v = make_double2(t.ox, t.oy);                // padding slots: benign, never used
+      if (i < n) {
+        const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
+        v = q;                                             // icp.py:32  src = copy(A)
+        if (op.init_pose)
+          v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
+                           ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
+      }
+      t.src[i] = v;
+    }
+    __syncwarp();
+
+    for (int it = 0; it < op.max_iterations; ++it) {       // icp.py:35
+      int32_t* hist = out.index_history
+          ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
+      double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int base = 0; base < n; base += 32 * SC) {
+        // ---- candidate sweep for SC sources per lane (icp.py:37-38)
+        float fx[SC], fy[SC];
+#pragma unroll
+        for (int k = 0; k < SC; ++k) {
+          const double2 s = t.src[base + k * 32 + lane];
+          fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
+        }
+        Candidates<SC> c;
+        warp_candidates<SC>(t, fx, fy, c);
+        // ---- exact decision in three straight-line phases so the SC matched-point loads
+        //      (global, L1/L2) and the SC float64 sqrt chains overlap instead of serialising
+        int j[SC];
+        bool amb[SC];
+        bool any_amb = false;
+#pragma unroll
+        for (int k = 0; k < SC; ++k) {
+          bool tie_in;
+          const int slot = in_group_argmin(t, c.group[k], fx[k], fy[k], tie_in);
+          j[k] = c.group[k] * kGroup + slot;
+          amb[k] = (base + k * 32 + lane < n) &&
+                   (tie_in || is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax));
+          any_amb |= amb[k];
+        }
+        if (__any_sync(kFull, any_amb)) {      // rare: warp-cooperative float64 scan
+#pragma unroll
+          for (int k = 0; k < SC; ++k) {
+            unsigned pending = __ballot_sync(kFull, amb[k]);
+            if (!pending) continue;
+            const double2 s = t.src[base + k * 32 + lane];
+            int jk = j[k];
+            while (pending) {
+              const int owner = __ffs(pending) - 1;
+              pending &= pending - 1;
+              const double qx = __shfl_sync(kFull, s.x, owner), qy = __shfl_sync(kFull, s.y, owner);
+              double ld = CUDART_INF;
+              int lj = 0x7fffffff;
+              for (int jj = lane; jj < m; jj += 32) {
+                const double d = dist2_f64(qx, qy, load_point(t.tgt, t.dtype, t.row_off + jj));
+                if (d < ld) { ld = d; lj = jj; }
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(kFull, ld, o);
+                const int oj = __shfl_xor_sync(kFull, lj, o);
+                if (od < ld || (od == ld && oj < lj)) { ld = od; lj = oj; }
+              }
+              if (lane == owner) jk = lj;
+            }
+            j[k] = jk;
+          }
+        }
+        // ---- gather (icp.py:39): all SC loads in flight before the first use
+        double2 bm[SC];
+#pragma unroll
+        for (int k = 0; k < SC; ++k) {
+          const int jj = (base + k * 32 + lane < n) ? j[k] : 0;
+          bm[k] = load_point(t.tgt, t.dtype, t.row_off + jj);
+        }
+        const double gate = op.max_corr_dist;
+        const bool use_gate = a.use_gate != 0;
+#pragma unroll
+        for (int k = 0; k < SC; ++k) {
+          const int i = base + k * 32 + lane;
+          if (i < n) {
+            const double2 s = t.src[i];
+            const double2 b = bm[k];
+            const double d2 = dist2_f64(s.x, s.y, b);
+            const double dist = sqrt(d2);
+            if (!use_gate || dist < gate) {
+              const double ax = s.x - t.ox, ay = s.y - t.oy;
+              const double qx = b.x - t.ox, qy = b.y - t.oy;
+              r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
+              r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
+              r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
+              r[8] += dist; r[9] += d2; r[10] += 1.0;
+            }
+            if (idx_out) idx_out[i] = j[k];
+            if (hist) hist[i] = j[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 11; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[q] += __shfl_xor_sync(kFull, r[q], o);
+      }
+      const double cnt = r[10];
+      if (cnt < 0.5) {            // every correspondence gated out: stop, search not counted
+        if (lane == 0) { ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->inl = 0; }
+        if (hist) for (int i = lane; i < n; i += 32) hist[i] = -1;
+        break;
+      }
+      const double inv = a.use_gate ? 1.0 / cnt : ctx->inv_n;
+      const double max_ = r[0] * inv, may_ = r[1] * inv;       // centroids rel. origin (icp.py:10-11)
+      const double mbx = r[2] * inv, mby = r[3] * inv;
+      const double mean_error = r[8] * inv;                    // icp.py:48
+      // closed-form 2D Kabsch: the proper rotation the SVD route (icp.py:17-23) returns
+      const double h00 = fma(-r[0], mbx, r[4]), h01 = fma(-r[0], mby, r[5]);
+      const double h10 = fma(-r[1], mbx, r[6]), h11 = fma(-r[1], mby, r[7]);
+      const double num = h01 - h10, den = h00 + h11;
+      const double h2 = fma(num, num, den * den);
+      double cs = 1.0, sn = 0.0;
+      if (h2 > 0.0) {
+        const double rh = rsqrt(h2);
+        cs = den * rh; sn = num * rh;
+      }
+      const double cax = t.ox + max_, cay = t.oy + may_;
+      const double tx = (t.ox + mbx) - (cs * cax - sn * cay);  // icp.py:25
+      const double ty = (t.oy + mby) - (sn * cax + cs * cay);
+      for (int i = lane; i < n; i += 32) {                     // apply (icp.py:45)
+        const double2 s = t.src[i];
+        t.src[i] = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
+      }
+      const bool converged = fabs(ctx->prev_error - mean_error) < op.tolerance;   // icp.py:49-50
+      __syncwarp();
+      if (lane == 0) {            // compose the cumulative pose, record the increment
+        const double R00 = ctx->R[0], R01 = ctx->R[1], R10 = ctx->R[2], R11 = ctx->R[3];
+        const double T0 = ctx->T[0], T1 = ctx->T[1];
+        ctx->R[0] = cs * R00 - sn * R10; ctx->R[1] = cs * R01 - sn * R11;
+        ctx->R[2] = sn * R00 + cs * R10; ctx->R[3] = sn * R01 + cs * R11;
+        ctx->T[0] = cs * T0 - sn * T1 + tx; ctx->T[1] = sn * T0 + cs * T1 + ty;
+        ctx->last[0] = cs; ctx->last[1] = sn; ctx->last[2] = tx; ctx->last[3] = ty;
+        ctx->err = mean_error; ctx->mean_d2 = r[9] * inv; ctx->inl = (int)(cnt + 0.5);
+        ctx->iters = it + 1;
+        ctx->prev_error = mean_error;                          // icp.py:51
+      }
+      __syncwarp();
+      if (converged) break;
+    }
+  }
+
+  const int iters = ctx->iters;
+  if (lane == 0) {
+    double* pt = out.pose_total + p * 6;
+    pt[0] = ctx->R[0]; pt[1] = ctx->R[1]; pt[2] = ctx->R[2]; pt[3] = ctx->R[3];
+    pt[4] = ctx->T[0]; pt[5] = ctx->T[1];
+    if (out.pose_last) {
+      double* pl = out.pose_last + p * 6;
+      pl[0] = ctx->last[0]; pl[1] = -ctx->last[1]; pl[2] = ctx->last[1]; pl[3] = ctx->last[0];
+      pl[4] = ctx->last[2]; pl[5] = ctx->last[3];
+    }
+    out.error[p] = ctx->err;
+    if (out.rmse) out.rmse[p] = sqrt(ctx->mean_d2);
+    if (out.inliers) out.inliers[p] = ctx->inl;
+    out.iterations[p] = iters;
+  }
+  if (idx_out) {
+    for (int i = lane; i < pr.src_pitch; i += 32)
+      if (i >= n || iters == 0) idx_out[i] = -1;
+  }
+  if (out.src_final) {
+    double2* dst = reinterpret_cast<double2*>(out.src_final) + p * pr.src_pitch;
+    for (int i = lane; i < pr.src_pitch; i += 32) {
+      double2 v = make_double2(0.0, 0.0);
+      if (i < n) {
+        if (ran) {
+          v = t.src[i];
+        } else {         // nothing ran: report the (pre-transformed) input
+          const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
+          v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
+                           ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
+        }
+      }
+      dst[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // kernel: scan preparation (process.py:38-52), one CTA per scan, order-preserving
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) polar_to_cartesian_kernel(
@@ -830,6 +1205,36 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   args.mcap = ls.mcap;
   args.use_gate = (opt->max_corr_dist > 0.0 && std::isfinite(opt->max_corr_dist)) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (env_int("B200ICP_ALIGN_BLOCK", 0) == 0) {
+    // warp-per-pair kernel: SC sources per lane per sweep, one-warp CTAs
+    int SC = env_int("B200ICP_FORCE_SC", 0);
+    if (SC != 2 && SC != 4 && SC != 6 && SC != 8 && SC != 12) {
+      // cost model: padded source slots, plus a per-sweep overhead that shrinks with the
+      // pass width (target LDS and loop control are shared by the SC sources of a lane).
+      // SC = 12 is compiled but never chosen: one 12-wide pass measured slower than two
+      // 6-wide passes on B200 (profiles/r1_kernel_tuning.md).
+      const int cand[4] = {8, 6, 4, 2};
+      double best_cost = 1e30;
+      SC = 8;
+      for (int q = 0; q < 4; ++q) {
+        const int span = 32 * cand[q];
+        const int slots = (prob->src_pitch + span - 1) / span * span;
+        const double cost = slots * (1.0 + 1.0 / cand[q]);
+        if (cost < best_cost) { best_cost = cost; SC = cand[q]; }
+      }
+    }
+    args.ncap = (prob->src_pitch + 32 * SC - 1) / (32 * SC) * (32 * SC);
+    LaunchShape ws = ls;
+    ws.warps = 1;
+    ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
+    switch (SC) {
+      case 2: return launch_pairs(icp_align_warp_kernel<2>, ws, args, st);
+      case 4: return launch_pairs(icp_align_warp_kernel<4>, ws, args, st);
+      case 6: return launch_pairs(icp_align_warp_kernel<6>, ws, args, st);
+      case 8: return launch_pairs(icp_align_warp_kernel<8>, ws, args, st);
+      default: return launch_pairs(icp_align_warp_kernel<12>, ws, args, st);
+    }
+  }
   B200ICP_DISPATCH(icp_align_kernel)
 }
 
