@@ -10,11 +10,13 @@ from .registration import (AlignResult, ScanTable, align_pairs, alloc_outputs,  
                            ffma_probe, nn_search, polar_to_cartesian)
 from .odometry import align_consecutive, chain_poses         # noqa: F401
 from .sharding import shard_range, triangle_pair, triangle_pair_count   # noqa: F401
+from .scan_to_map import MapShard, ScanToMap, ScanToMapResult, scan_to_map_icp   # noqa: F401
 from . import scan_io                                          # noqa: F401
 
 __all__ = [
     "B200IcpError", "lib", "library_path", "IcpOutput", "icp", "icp_full", "nearest_neighbors",
     "registration_p2p", "AlignResult", "ScanTable", "align_pairs", "alloc_outputs", "ffma_probe",
     "nn_search", "polar_to_cartesian", "align_consecutive", "chain_poses", "shard_range",
-    "triangle_pair", "triangle_pair_count", "scan_io",
+    "triangle_pair", "triangle_pair_count", "scan_io", "MapShard", "ScanToMap", "ScanToMapResult",
+    "scan_to_map_icp",
 ]

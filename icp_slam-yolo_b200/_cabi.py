@@ -47,6 +47,15 @@ class Outputs(C.Structure):
     ]
 
 
+class S2MShard(C.Structure):
+    _fields_ = [
+        ("points", C.c_void_p), ("m", C.c_int64), ("global_offset", C.c_int64),
+        ("dtype", C.c_int32), ("reserved", C.c_int32),
+        ("cx", C.c_void_p), ("cy", C.c_void_p), ("chunk_origin", C.c_void_p),
+        ("chunk_radius", C.c_void_p),
+    ]
+
+
 # symbol -> (restype, argtypes); must list EVERY function include/b200icp.h declares
 SYMBOLS = {
     "b200icp_version": (C.c_int, []),
@@ -59,6 +68,15 @@ SYMBOLS = {
     "b200icp_polar_to_cartesian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200icp_ffma_probe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_void_p]),
+    "b200icp_s2m_chunk": (C.c_int, []),
+    "b200icp_s2m_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
+    "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p]),
+    "b200icp_s2m_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200icp_s2m_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -1144,6 +1144,9 @@ int launch_pairs(Kern kern, const LaunchShape& ls, const KernelArgs& args, cudaS
 
 }  // namespace
 
+// shared with scan2map.cu (C++ linkage: not part of the C ABI)
+void b200icp_set_error_str(const char* msg) { set_error("%s", msg); }
+
 extern "C" {
 
 int b200icp_version(void) { return B200ICP_VERSION_MAJOR * 1000 + B200ICP_VERSION_MINOR; }

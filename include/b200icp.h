@@ -146,6 +146,57 @@ int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_
                                int32_t raw_pitch, double* xy_out, int32_t* len_out,
                                int32_t out_pitch, void* stream);
 
+/* ---- scan-to-map ICP: a scan of a few thousand points against a map of millions, sharded
+ * contiguously across GPUs (one process per GPU).  The scan-to-local-map call shape of
+ * duc/ICP_LIDAR/mainn.py:297-318 / slam_offline.py:366-392 with the point-to-point loop of
+ * labels_segmentation/icp.py:28-53.  Per iteration and rank:
+ *     b200icp_s2m_search  -> records[n]   exact nearest map point of THIS shard per scan point
+ *     (caller)               all-gather of the records of every rank  -> records_all[ranks][n]
+ *     b200icp_s2m_update  -> global winner per point (distance, then lowest global index),
+ *                            pose solve, apply, convergence; bit-identical on every rank.
+ * Both are asynchronous and become no-ops once state->done is set, so a fixed-length loop needs
+ * no host synchronisation. */
+typedef struct b200icp_s2m_shard {
+  const void* points;      /* [m][2] map points of this shard (dtype below)                    */
+  int64_t m;               /* points in this shard                                             */
+  int64_t global_offset;   /* index of points[0] in the whole map (contiguous sharding)        */
+  int32_t dtype;           /* b200icp_dtype                                                    */
+  int32_t reserved;
+  /* filled by b200icp_s2m_prepare_map; caller-allocated, mcap = m rounded up to s2m_chunk(): */
+  float* cx;               /* [mcap] chunk-centred float32 x (+inf sentinels)                  */
+  float* cy;               /* [mcap]                                                           */
+  double* chunk_origin;    /* [mcap / chunk][2]                                                */
+  float* chunk_radius;     /* [mcap / chunk] max |centred coordinate|                          */
+} b200icp_s2m_shard;
+
+typedef struct b200icp_s2m_record {   /* 32 bytes, one per scan point and rank */
+  double d2;               /* exact float64 squared distance to the shard's nearest point      */
+  int64_t gidx;            /* its global map index                                             */
+  double bx, by;           /* its coordinates (so no rank needs another rank's shard)          */
+} b200icp_s2m_record;
+
+typedef struct b200icp_s2m_state {    /* device-resident, 136 bytes */
+  double pose_total[6];    /* R00 R01 R10 R11 tx ty, cumulative                                */
+  double pose_last[6];     /* last increment (what icp() returns, icp.py:53)                   */
+  double error;            /* mean NN distance of the last search (icp.py:48)                  */
+  double mean_d2;
+  double prev_error;
+  int32_t iterations, inliers, done, reserved;
+} b200icp_s2m_state;
+
+int b200icp_s2m_chunk(void);                                   /* 1024                          */
+int64_t b200icp_s2m_workspace_bytes(int32_t n_scan, int64_t m);
+int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream);
+/* src64 [n][2] float64 scan state (written), state (written) */
+int b200icp_s2m_init(const void* scan, int32_t dtype, int32_t n, const double* init_pose /*[6]|NULL*/,
+                     double* src64, b200icp_s2m_state* state, void* stream);
+int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int32_t n,
+                       b200icp_s2m_record* records, void* workspace, int64_t workspace_bytes,
+                       const b200icp_s2m_state* state, void* stream);
+int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, double* src64,
+                       int32_t n, int32_t max_iterations, double tolerance, double max_corr_dist,
+                       int32_t* idx_out /*[n]|NULL*/, b200icp_s2m_state* state, void* stream);
+
 /*
  * FP32 FFMA throughput probe used as the roofline denominator of the NN phase
  * (MEASURED_PEAKS.json carries no FP32 figure).  Launches one kernel doing

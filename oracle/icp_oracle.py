@@ -296,3 +296,43 @@ def synth_room_batch(first_pair, count, n_points=360, dtype=np.float32, with_tru
     if with_truth:
         return src, tgt, theta, t
     return src, tgt
+
+
+# ----------------------------------------------------------------------------
+# config 5: scan-to-map
+# ----------------------------------------------------------------------------
+def _polyline_world(seed, n_vertices=24):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ang = np.sort(rng.uniform(0.0, 2.0 * np.pi, size=n_vertices))
+    rad = rng.uniform(8000.0, 20000.0, size=n_vertices)
+    v = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1)
+    seg = np.roll(v, -1, axis=0) - v
+    length = np.hypot(seg[:, 0], seg[:, 1])
+    return rng, v, seg, np.concatenate([[0.0], np.cumsum(length)])
+
+
+def _sample_polyline(v, seg, cum, s):
+    k = np.clip(np.searchsorted(cum, s, side="right") - 1, 0, len(seg) - 1)
+    f = (s - cum[k]) / (cum[k + 1] - cum[k])
+    return v[k] + seg[k] * f[:, None]
+
+
+def synth_map(m, seed=5, dtype=np.float32):
+    """Map of config 5: m points in order along a seeded closed random polyline (a room of
+    8-20 m radius), N(0, 5 mm) noise on both coordinates.  Generated in float64, cast."""
+    rng, v, seg, cum = _polyline_world(seed)
+    s = (np.arange(m, dtype=np.float64) + 0.5) * (cum[-1] / m)
+    pts = _sample_polyline(v, seg, cum, s) + rng.normal(0.0, 5.0, size=(m, 2))
+    return pts.astype(dtype)
+
+
+def synth_scan_for_map(n, seed=5, scan_seed=77, theta=0.02, t=(35.0, -20.0), dtype=np.float32):
+    """n noisy observations of the same polyline, expressed in a sensor frame that is rotated by
+    ``theta`` and shifted by ``t`` against the map frame (so ICP should recover about that)."""
+    _, v, seg, cum = _polyline_world(seed)
+    rng = np.random.Generator(np.random.PCG64(scan_seed))
+    s = np.sort(rng.uniform(0.0, cum[-1], size=n))
+    world = _sample_polyline(v, seg, cum, s) + rng.normal(0.0, 5.0, size=(n, 2))
+    c, sn = np.cos(theta), np.sin(theta)
+    wx, wy = world[:, 0] - t[0], world[:, 1] - t[1]
+    return np.stack([wx * c + wy * sn, wy * c - wx * sn], axis=1).astype(dtype)

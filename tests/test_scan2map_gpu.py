@@ -1,0 +1,80 @@
+"""GPU parity of the scan-to-map path (config 5 at reduced size) against the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import icp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import icp_slam_yolo_b200 as m
+    assert torch.cuda.is_available()
+    m.lib()
+    return m
+
+
+def _shards(b200, map_pts, n_shards):
+    out = []
+    for g in range(n_shards):
+        b, e = b200.shard_range(len(map_pts), g, n_shards)
+        out.append(b200.MapShard(torch.from_numpy(map_pts[b:e]).cuda(), global_offset=b))
+    return out
+
+
+@pytest.mark.parametrize("m_points,n_scan,n_shards,dtype", [
+    (1 << 18, 8192, 4, np.float32),      # parity on the reduced instance M = 2^18
+    (50000, 1000, 3, np.float64),        # ragged: shard sizes not multiples of the chunk
+    (777, 130, 1, np.float64),           # a single partial chunk
+])
+def test_scan_to_map_matches_oracle_every_iteration(b200, m_points, n_scan, n_shards, dtype):
+    map_pts = orc.synth_map(m_points, dtype=dtype)
+    scan = orc.synth_scan_for_map(n_scan, dtype=dtype)
+    iters = 6
+    o = orc.icp_extended(scan, map_pts, iters, -1.0)            # KD-tree oracle, forced iterations
+    run = b200.scan_to_map.ScanToMapLocalShards(_shards(b200, map_pts, n_shards), n_scan)
+    run.init(torch.from_numpy(scan).cuda())
+    for it in range(iters):
+        run.step(iters, -1.0)
+        idx = run.indices.cpu().numpy()
+        assert np.array_equal(idx, o.indices[it]), f"iteration {it}: {np.sum(idx != o.indices[it])} indices differ"
+    r = run.result()
+    assert r.iterations == iters
+    assert abs(math.atan2(r.R[1, 0], r.R[0, 0]) - math.atan2(o.R_tot[1, 0], o.R_tot[0, 0])) < 1e-9
+    assert np.max(np.abs(r.t - o.t_tot)) < 1e-6 and abs(r.error - o.error) < 1e-9 * max(1.0, o.error)
+    assert np.allclose(r.src.cpu().numpy(), o.src, rtol=0, atol=1e-6)
+
+
+def test_scan_to_map_convergence_gate_and_init_pose(b200):
+    map_pts = orc.synth_map(60000, dtype=np.float64)
+    scan = orc.synth_scan_for_map(2000, dtype=np.float64)
+    th = 0.01
+    init = [math.cos(th), -math.sin(th), math.sin(th), math.cos(th), 10.0, -5.0]
+    for gate in (None, 40.0):
+        o = orc.icp_extended(scan, map_pts, 25, 1e-5, init_pose=(np.array(init[:4]).reshape(2, 2), np.array(init[4:])),
+                             max_corr_dist=gate)
+        shard = b200.MapShard(torch.from_numpy(map_pts).cuda())
+        r = b200.scan_to_map_icp(torch.from_numpy(scan).cuda(), shard, 25, 1e-5, init_pose=init,
+                                 max_corr_dist=gate, want_indices=True)
+        assert r.iterations == o.iterations and r.inliers == round(o.fitness * len(scan))
+        assert np.array_equal(r.indices.cpu().numpy(), o.indices[-1])
+        assert np.allclose(r.R, o.R_tot, atol=1e-9) and np.allclose(r.t, o.t_tot, atol=1e-6)
+        assert abs(r.error - o.error) < 1e-9 * max(1.0, o.error) and abs(r.rmse - o.rmse) < 1e-9 * max(1.0, o.rmse)
+        assert np.allclose(r.R_last, o.R_last, atol=1e-9) and np.allclose(r.t_last, o.t_last, atol=1e-6)
+
+
+def test_scan_to_map_duplicates_resolve_to_lowest_global_index(b200):
+    """Exact float64 ties across shards: the winner is the lowest GLOBAL index."""
+    rng = np.random.default_rng(1)
+    base = rng.uniform(-5000, 5000, size=(3000, 2))
+    map_pts = np.concatenate([base, base, base])              # every point exists in 3 shards
+    scan = base[:512] + rng.normal(0, 1.0, size=(512, 2))
+    run = b200.scan_to_map.ScanToMapLocalShards(_shards(b200, map_pts, 3), 512)
+    run.init(torch.from_numpy(scan).cuda())
+    run.step(1, -1.0)
+    _, ref = orc.nn_bruteforce(scan, map_pts)
+    assert np.array_equal(run.indices.cpu().numpy(), ref) and ref.max() < 3000
