@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "odometry", "allpairs", "scan2map"],
+                    help="pairs = the headline configs[2] (default); the others are BASELINE.json "
+                         "configs[1], [3] and [4], reported with the same JSON shape")
+    ap.add_argument("--map-points", type=int, default=1 << 24, help="scan2map: total map points")
+    ap.add_argument("--scan-points", type=int, default=8192)
     return ap.parse_args()
 
 
@@ -288,8 +293,6 @@ def run_b200(args):
                "api": "icp_slam_yolo_b200.registration.HostPipeline.run (16 chunks, copy/compute overlap)"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     flops = P * PAIR_EVALS_PER_ALIGNMENT * FLOP_PER_PAIR_EVAL
@@ -310,7 +313,7 @@ def run_b200(args):
                    "parallelism": "pairs sharded by contiguous index range, no collective"},
         "gpu_launches": args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "fp32", "kernel": "icp_align_kernel<3>", "achieved": achieved_tflops,
+        "roofline": {"bound": "fp32", "kernel": "icp_align_warp_kernel<6>", "achieved": achieved_tflops,
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                      "peak_source": "b200icp_ffma_probe measured live (dependent-FFMA chains, all SMs)",
                      "algorithmic_flop_per_launch": flops, "kernel_ms": kernel_ms, "traffic": None,
@@ -327,12 +330,245 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs[1], [3], [4]); same timing rules, same JSON shape
+# ------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return world, rank, local, dev, barrier, max_over_ranks
+
+
+def _timed(step, steps, warmup, barrier, max_over_ranks):
+    import torch
+    for _ in range(max(3, warmup)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+def _fixture_scans():
+    from icp_slam_yolo_b200 import scan_io
+    return scan_io.unpack_fixture(os.path.join(ROOT, "tests", "golden", "scan_data_1_packed.npz"))
+
+
+def run_odometry(args):
+    """configs[1]: Scan_data_1 sequence odometry, all 1,830 consecutive pairs (k+1 -> k),
+    max_iterations 30, tolerance 1e-5, one launch; the bundled recording ships as the lossless
+    fixture tests/golden/scan_data_1_packed.npz."""
+    import torch
+    import icp_slam_yolo_b200 as m
+    from oracle import icp_oracle as orc
+    raw = _fixture_scans()
+    # CPU: the oracle port on one core (the reference as shipped) -- before CUDA init
+    cart = [np.ascontiguousarray(orc.polar_to_cartesian(r)[:, :2]) for r in raw]
+    t0 = time.perf_counter()
+    its = sum(orc.icp_extended(cart[p + 1], cart[p], 30, 1e-5, keep_history=False).iterations
+              for p in range(len(cart) - 1))
+    cpu_wall = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for r in raw[:200]:
+        orc.polar_to_cartesian_loop(r)
+    cpu_prep = (time.perf_counter() - t0) * len(raw) / 200.0
+    world, rank, local, dev, barrier, max_over_ranks = _dist_setup()
+    n_pairs = len(raw) - 1
+    h_raw, h_len = m.scan_io.raw_table(raw, pin=True)
+    table = m.scan_io.prepare_scans(raw, device=dev)
+    out = m.alloc_outputs(n_pairs, table.pitch, dev)
+    fp32_peak = m.ffma_probe()
+
+    def step():
+        m.align_consecutive(table, max_iterations=30, tolerance=1e-5, out=out)
+
+    ms = _timed(step, args.steps, args.warmup, barrier, max_over_ranks)
+    gpu_its = int(out.iterations.sum().item())
+
+    def e2e_step():       # raw polar rows on the host -> poses on the host
+        d_raw = h_raw.to(dev, non_blocking=True)
+        d_len = h_len.to(dev, non_blocking=True)
+        tb = m.polar_to_cartesian(d_raw, d_len)
+        res = m.align_consecutive(tb, max_iterations=30, tolerance=1e-5, out=out)
+        return m.chain_poses(res.pose_total)             # D2H of [1830,6] + host prefix composition
+
+    e2e_ms = _timed(e2e_step, args.steps, args.warmup, barrier, max_over_ranks)
+    lens = table.lengths.cpu().numpy().astype(np.int64)
+    its_np = out.iterations.cpu().numpy().astype(np.int64)
+    evals = float(np.sum(lens[1:] * lens[:-1] * its_np))
+    if rank != 0:
+        return
+    line = {
+        "metric": "ICP alignments/sec (Scan_data_1 sequence odometry, 1,830 consecutive pairs)",
+        "value": n_pairs / (ms * 1e-3), "unit": "alignments/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "replicas",
+        "vs_baseline": None, "dtype": "f32 search + f64 state", "data": "bundled recording (fixture)",
+        "nn_pairs_per_s": evals / (ms * 1e-3),
+        "config": {"workload": "configs[1]: full Scan_data_1 sequence odometry, 1,830 pairs, max_iterations 30, "
+                               "tolerance 1e-5, ragged 11..196 points", "iterations_total": gpu_its,
+                   "l2": "inputs (5.7 MB) fit L2: a 64 MB buffer is NOT flushed between steps; noted"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "fp32", "kernel": "icp_align_warp_kernel", "achieved": evals * 5 / (ms * 1e-3) / 1e12,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": evals * 5 / (ms * 1e-3) / 1e12 / fp32_peak,
+                     "traffic": None, "note": "tiny ragged problems: 1,830 one-warp CTAs = 0.77 waves"},
+        "e2e": {"value": n_pairs / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h_raw.numel() * 8 + h_len.numel() * 4),
+                "d2h_bytes_per_step": n_pairs * 48,
+                "api": "raw polar rows (host) -> polar_to_cartesian -> align_consecutive -> chain_poses (host)"},
+        "cpu_baseline": {"value": n_pairs / cpu_wall, "unit": "alignments/s", "cores": 1, "kind": "port",
+                         "sample": f"all 1,830 pairs, oracle port of icp.py:5-53, {cpu_wall:.3f} s wall "
+                                   f"(+ {cpu_prep:.3f} s for process.py:38-52's row loop); {its} iterations; {cpu_model()}",
+                         "wall_s": cpu_wall, "prep_wall_s": cpu_prep},
+        "gpu_wall_fraction_of_cpu": {"kernel_only": ms * 1e-3 / cpu_wall,
+                                     "e2e_incl_prep": e2e_ms * 1e-3 / (cpu_wall + cpu_prep)},
+    }
+    assert gpu_its == its, (gpu_its, its)
+    print(json.dumps(line), flush=True)
+
+
+def run_allpairs(args):
+    """configs[3]: all-pairs loop-closure candidates over 4,096 synthetic scans (8,386,560 pairs),
+    30 forced iterations, pairs enumerated row-major (i<j) and split into contiguous ranges."""
+    import torch
+    import icp_slam_yolo_b200 as m
+    from oracle import icp_oracle as orc
+    world, rank, local, dev, barrier, max_over_ranks = _dist_setup()
+    n_scans = 4096
+    scans = orc.synth_trajectory_scans(n_scans)
+    table = m.ScanTable(torch.from_numpy(scans).to(dev))
+    total = m.triangle_pair_count(n_scans) if args.pairs == 65536 else min(args.pairs, m.triangle_pair_count(n_scans))
+    b, e = m.shard_range(total, rank, world)
+    mine = e - b
+    out = m.alloc_outputs(mine, N_POINTS, dev)
+    fp32_peak = m.ffma_probe()
+
+    def step():
+        m.align_pairs(table, table, pairing="triangle", first_pair=b, n_pairs=mine,
+                      max_iterations=ITERS, tolerance=-1.0, out=out)
+
+    ms = _timed(step, args.steps, args.warmup, barrier, max_over_ranks)
+    if rank != 0:
+        return
+    value = total / (ms * 1e-3)
+    line = {
+        "metric": "ICP alignments/sec (all-pairs loop closure, 360-pt scans, 30 iters)",
+        "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 search + f64 state", "data": "synthetic",
+        "nn_pairs_per_s": value * PAIR_EVALS_PER_ALIGNMENT,
+        "config": {"workload": "configs[3]: all-pairs loop-closure candidate ICP over 4,096 synthetic scans",
+                   "pairs_total": total, "pairs_this_rank": mine, "scan_table_bytes": int(scans.nbytes),
+                   "l2": "scan table (11.8 MB) is L2 resident by design; outputs 48 B/pair stream to HBM",
+                   "parallelism": "triangular pair index split in contiguous ranges, no collective"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "fp32", "kernel": "icp_align_warp_kernel<6>",
+                     "achieved": mine * PAIR_EVALS_PER_ALIGNMENT * 5 / (ms * 1e-3) / 1e12, "peak": fp32_peak,
+                     "unit": "TFLOP/s",
+                     "frac": mine * PAIR_EVALS_PER_ALIGNMENT * 5 / (ms * 1e-3) / 1e12 / fp32_peak, "traffic": None},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_scan2map(args):
+    """configs[4]: 8,192-point scan against a 2^24-point map sharded contiguously across the
+    ranks; 30 forced iterations; one all-gather of 32-byte records per iteration."""
+    import torch
+    import icp_slam_yolo_b200 as m
+    from oracle import icp_oracle as orc
+    world, rank, local, dev, barrier, max_over_ranks = _dist_setup()
+    M, N = args.map_points, args.scan_points
+    b, e = m.shard_range(M, rank, world)
+    full = orc.synth_map(M)                               # seeded: every rank draws the same map
+    shard = m.MapShard(torch.from_numpy(full[b:e]).to(dev), global_offset=b)
+    del full
+    scan = torch.from_numpy(orc.synth_scan_for_map(N)).to(dev)
+    s2m = m.ScanToMap(shard, N)
+    fp32_peak = m.ffma_probe()
+
+    def step():
+        s2m.run(scan, max_iterations=ITERS, tolerance=-1.0, sync=False)
+
+    ms = _timed(step, args.steps, args.warmup, barrier, max_over_ranks)
+    res = s2m.result()
+    assert res.iterations == ITERS
+    # sweep kernel alone (the dominant kernel), CUDA events on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = s2m.state.clone()
+    s2m.state[16] = 0.0                                    # clear `done` so the kernels run
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        s2m.search()
+    e1.record()
+    torch.cuda.synchronize()
+    search_ms = e0.elapsed_time(e1) / 5
+    s2m.state.copy_(st)
+    if rank != 0:
+        return
+    evals_per_iter = float(N) * float(M)
+    line = {
+        "metric": "scan-to-map ICP alignments/sec (8,192-pt scan vs 16M-pt map, 30 iters)",
+        "value": 1.0 / (ms * 1e-3), "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 search + f64 state", "data": "synthetic",
+        "nn_pairs_per_s": evals_per_iter * ITERS / (ms * 1e-3),
+        "config": {"workload": "configs[4]: scan-to-map ICP, %d-point scan vs %d-point map, 30 forced iterations" % (N, M),
+                   "map_points_this_rank": e - b,
+                   "l2": "map shard SoA (%.0f MB) streams from L2/HBM every iteration" % ((e - b) * 8 / 1e6),
+                   "parallelism": "map sharded contiguously; all_gather of 32 B records per iteration (%d B per rank)" % (N * 32),
+                   "final_error_mm": res.error},
+        "gpu_launches": args.steps * s2m.launches,
+        "roofline": {"bound": "fp32", "kernel": "s2m_sweep_kernel (+ resolve/exact)",
+                     "achieved": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "frac": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12 / fp32_peak,
+                     "kernel_ms": search_ms, "traffic": None},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "odometry":
+        run_odometry(args)
+    elif args.workload == "allpairs":
+        run_allpairs(args)
+    elif args.workload == "scan2map":
+        run_scan2map(args)
     else:
         run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

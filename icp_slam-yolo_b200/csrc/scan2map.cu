@@ -11,7 +11,7 @@
 //                        lower bounds of the best and of the runner-up group, best group
 //   s2m_resolve_kernel   merge segments, FP32 in-group argmin, exact float64 distance of the
 //                        winner; sources whose runner-up may beat the winner go to a list
-//   s2m_exact_kernel     float64 brute force over the whole shard for the listed sources
+//   s2m_exact_*_kernel   float64 brute force over the whole shard for the listed sources
 //   s2m_update_kernel    after the records of all ranks are gathered: per point the global
 //                        winner (smaller distance, then lower global index), the centred sums,
 //                        closed-form pose, apply, convergence -- identical on every rank
@@ -306,23 +306,47 @@ __global__ void __launch_bounds__(128) s2m_resolve_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// exact: float64 brute force over the shard for the listed sources (lowest index on ties)
+// exact: float64 brute force over the shard for the listed sources (lowest index on ties).
+// The shard is cut into kExactParts slices; CTA (p, y) scans slice p for the listed sources
+// e = y, y + gridDim.y, ... with four independent loads in flight per thread, so even a single
+// listed source is spread over kExactParts SMs instead of streaming the shard through one.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) s2m_exact_kernel(
-    const void* points, int dtype, int64_t m, int64_t global_offset, const double* __restrict__ src64,
+constexpr int kExactParts = 64;
+constexpr int kExactRows = 8;
+
+struct ExactPartial {
+  double d2;
+  long long j;
+};
+
+__global__ void __launch_bounds__(256) s2m_exact_scan_kernel(
+    const void* points, int dtype, int64_t m, const double* __restrict__ src64,
     const int32_t* __restrict__ amb_list, const int32_t* __restrict__ amb_count,
-    b200icp_s2m_record* __restrict__ records, const b200icp_s2m_state* __restrict__ state) {
+    ExactPartial* __restrict__ exact_partials, const b200icp_s2m_state* __restrict__ state) {
   __shared__ double sd[8];
   __shared__ long long sj[8];
   if (state->done) return;
   const int count = *amb_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = blockIdx.x; e < count; e += gridDim.x) {
+  const int64_t slice = (m + kExactParts - 1) / kExactParts;
+  const int64_t j_begin = (int64_t)blockIdx.x * slice, j_end = min(m, j_begin + slice);
+  for (int e = blockIdx.y; e < count; e += gridDim.y) {
     const int i = amb_list[e];
     const double sx = src64[2 * i], sy = src64[2 * i + 1];
     double bd = CUDART_INF;
     long long bj = 0x7fffffffffffffffLL;
-    for (int64_t j = tid; j < m; j += blockDim.x) {
+    int64_t j = j_begin + tid;
+    for (; j + 3 * 256 < j_end; j += 4 * 256) {          // ascending j per thread
+      const double2 q0 = load_point(points, dtype, j), q1 = load_point(points, dtype, j + 256);
+      const double2 q2 = load_point(points, dtype, j + 512), q3 = load_point(points, dtype, j + 768);
+      const double d0 = dist2_f64(sx, sy, q0), d1 = dist2_f64(sx, sy, q1);
+      const double d2 = dist2_f64(sx, sy, q2), d3 = dist2_f64(sx, sy, q3);
+      if (d0 < bd) { bd = d0; bj = j; }
+      if (d1 < bd) { bd = d1; bj = j + 256; }
+      if (d2 < bd) { bd = d2; bj = j + 512; }
+      if (d3 < bd) { bd = d3; bj = j + 768; }
+    }
+    for (; j < j_end; j += 256) {
       const double d = dist2_f64(sx, sy, load_point(points, dtype, j));
       if (d < bd) { bd = d; bj = j; }
     }
@@ -337,12 +361,42 @@ __global__ void __launch_bounds__(256) s2m_exact_kernel(
     if (tid == 0) {
       for (int w = 1; w < 8; ++w)
         if (sd[w] < bd || (sd[w] == bd && sj[w] < bj)) { bd = sd[w]; bj = sj[w]; }
+      ExactPartial r;
+      r.d2 = bd; r.j = bj;
+      exact_partials[(int64_t)e * kExactParts + blockIdx.x] = r;
+    }
+    __syncthreads();
+  }
+}
+
+// one warp per listed source: lexicographic (distance, index) minimum over the slices
+__global__ void __launch_bounds__(256) s2m_exact_reduce_kernel(
+    const void* points, int dtype, int64_t global_offset, const int32_t* __restrict__ amb_list,
+    const int32_t* __restrict__ amb_count, const ExactPartial* __restrict__ exact_partials,
+    b200icp_s2m_record* __restrict__ records, const b200icp_s2m_state* __restrict__ state) {
+  if (state->done) return;
+  const int count = *amb_count;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < count; e += warps) {
+    double bd = CUDART_INF;
+    long long bj = 0x7fffffffffffffffLL;
+    for (int p = lane; p < kExactParts; p += 32) {
+      const ExactPartial r = exact_partials[(int64_t)e * kExactParts + p];
+      if (r.d2 < bd || (r.d2 == bd && r.j < bj)) { bd = r.d2; bj = r.j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(kFull, bd, o);
+      const long long oj = __shfl_xor_sync(kFull, bj, o);
+      if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+    }
+    if (lane == 0) {
       const double2 b = load_point(points, dtype, bj);
       b200icp_s2m_record rec;
       rec.d2 = bd; rec.gidx = global_offset + bj; rec.bx = b.x; rec.by = b.y;
-      records[i] = rec;
+      records[amb_list[e]] = rec;
     }
-    __syncthreads();
   }
 }
 
@@ -493,7 +547,8 @@ int64_t b200icp_s2m_workspace_bytes(int32_t n_scan, int64_t m) {
   if (sms < 1) sms = 148;
   const int64_t n_seg = segments_for((int)n_chunks, n_scan, sms);
   const int64_t list_bytes = ((int64_t)n_scan * 4 + 64 + 127) / 128 * 128;
-  return list_bytes + n_seg * (int64_t)n_scan * (int64_t)sizeof(Partial);
+  return list_bytes + n_seg * (int64_t)n_scan * (int64_t)sizeof(Partial) +
+         (int64_t)n_scan * kExactParts * (int64_t)sizeof(ExactPartial);
 }
 
 int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream) {
@@ -552,10 +607,14 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int3
       amb_count, state);
   rc = cuda_check("s2m_resolve_kernel");
   if (rc) return rc;
-  s2m_exact_kernel<<<2 * sms, 256, 0, st>>>(shard->points, shard->dtype, shard->m,
-                                            shard->global_offset, src64, amb_list, amb_count,
-                                            records, state);
-  return cuda_check("s2m_exact_kernel");
+  ExactPartial* exact_partials = reinterpret_cast<ExactPartial*>(partials + (int64_t)n_seg * n);
+  s2m_exact_scan_kernel<<<dim3(kExactParts, kExactRows), 256, 0, st>>>(
+      shard->points, shard->dtype, shard->m, src64, amb_list, amb_count, exact_partials, state);
+  rc = cuda_check("s2m_exact_scan_kernel");
+  if (rc) return rc;
+  s2m_exact_reduce_kernel<<<32, 256, 0, st>>>(shard->points, shard->dtype, shard->global_offset,
+                                              amb_list, amb_count, exact_partials, records, state);
+  return cuda_check("s2m_exact_reduce_kernel");
 }
 
 int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, double* src64,

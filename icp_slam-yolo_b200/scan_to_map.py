@@ -102,7 +102,7 @@ class ScanToMap:
                                        _ptr(self.records), _ptr(self.workspace),
                                        self.workspace.numel(), _ptr(self.state), _stream_ptr(stream))
         _cabi.check(rc, "b200icp_s2m_search")
-        self.launches += 3
+        self.launches += 4
 
     def run(self, scan: torch.Tensor, *, max_iterations: int = 20, tolerance: float = 1e-5,
             init_pose=None, max_corr_dist: Optional[float] = None, sync: bool = True):
@@ -123,7 +123,8 @@ class ScanToMap:
             for _ in range(int(max_iterations)):
                 self.search()
                 if self.world > 1:
-                    dist.all_gather_into_tensor(self.records_all, self.records, group=self.group)
+                    dist.all_gather_into_tensor(self.records_all.view(self.world * self.n, 4),
+                                                self.records, group=self.group)
                     rec_all, ranks = self.records_all, self.world
                 else:
                     rec_all, ranks = self.records, 1

@@ -336,3 +336,29 @@ def synth_scan_for_map(n, seed=5, scan_seed=77, theta=0.02, t=(35.0, -20.0), dty
     c, sn = np.cos(theta), np.sin(theta)
     wx, wy = world[:, 0] - t[0], world[:, 1] - t[1]
     return np.stack([wx * c + wy * sn, wy * c - wx * sn], axis=1).astype(dtype)
+
+
+# ----------------------------------------------------------------------------
+# config 4: all-pairs loop-closure candidates
+# ----------------------------------------------------------------------------
+def synth_trajectory_scans(n_scans, n_points=360, seed=4096, dtype=np.float32):
+    """n_scans scans of ONE star-convex room (same family as config 3) seen from a seeded
+    random-walk trajectory: step ~ N(0, 30 mm), heading step ~ N(0, 0.01 rad); every scan is
+    the room boundary at n_points world directions + N(0, 5 mm) range noise, expressed in the
+    sensor frame.  Returns [n_scans, n_points, 2]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    amp = rng.uniform(0.0, 600.0, size=4)
+    psi = rng.uniform(0.0, 2.0 * np.pi, size=4)
+    steps = rng.normal(0.0, 30.0, size=(n_scans, 2))
+    dth = rng.normal(0.0, 0.01, size=n_scans)
+    pos = np.cumsum(steps, axis=0)
+    th = np.cumsum(dth)
+    phi = np.deg2rad(np.arange(n_points, dtype=np.float64) * (360.0 / n_points))[None, :]
+    r = np.full((1, n_points), 3000.0)
+    for k in range(4):
+        r = r + amp[k] * np.sin((k + 1.0) * phi + psi[k])
+    r = r + rng.normal(0.0, 5.0, size=(n_scans, n_points))
+    wx = r * np.cos(phi) - pos[:, 0:1]
+    wy = r * np.sin(phi) - pos[:, 1:2]
+    c, s = np.cos(th)[:, None], np.sin(th)[:, None]
+    return np.stack([wx * c + wy * s, wy * c - wx * s], axis=2).astype(dtype)
