@@ -636,13 +636,17 @@ struct WarpTile {
   float* fy;            // [mcap]
   float* ft;            // [mcap] |centred|^2, +inf sentinels
   double2* src;         // [ncap] float64 source state
+  float* gcx;           // [mcap/8] bounding circle of each group of 8 targets (pruned sweep)
+  float* gcy;
+  float* grad;
   double ox, oy;
   float tmax;
   int m, mcap, ngroups;
 };
 
 __host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap) {
-  return (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + 160 /* WarpCtx */;
+  return (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + 160 /* WarpCtx */ +
+         (size_t)(mcap / kGroup) * 3 * sizeof(float);
 }
 
 __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
@@ -672,6 +676,29 @@ __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
   t.tmax = amax;
+  __syncwarp();
+  // bounding circle of every group (valid targets only), radius rounded up
+  for (int g = lane; g < t.ngroups; g += 32) {
+    float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
+    for (int u = 0; u < kGroup; ++u) {
+      const int j = g * kGroup + u;
+      if (j < t.m) {
+        x0 = fminf(x0, t.fx[j]); x1 = fmaxf(x1, t.fx[j]);
+        y0 = fminf(y0, t.fy[j]); y1 = fmaxf(y1, t.fy[j]);
+      }
+    }
+    const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
+    float r2 = 0.f;
+    for (int u = 0; u < kGroup; ++u) {
+      const int j = g * kGroup + u;
+      if (j < t.m) {
+        const float dx = t.fx[j] - cx, dy = t.fy[j] - cy;
+        r2 = fmaxf(r2, fmaf(dx, dx, dy * dy));
+      }
+    }
+    t.gcx[g] = cx; t.gcy[g] = cy;
+    t.grad[g] = sqrtf(r2) * 1.000004f + 1e-30f;
+  }
   __syncwarp();
 }
 
@@ -707,6 +734,113 @@ __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (
       const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
                             fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
       track<S>(c, k, m, g);
+    }
+  }
+}
+
+// One group of 8 targets against the S sources of a lane (expanded form, packed FFMA2).
+template <int S>
+__device__ __forceinline__ void eval_group(const WarpTile& t, int g, const float (&a)[S],
+                                           const float (&b)[S], Candidates<S>& c) {
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
+  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
+  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(t.ft);
+  const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
+  const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
+  const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
+    const float2 e01 = __ffma2_rn(ak, make_float2(xa.x, xa.y), __ffma2_rn(bk, make_float2(ya.x, ya.y), make_float2(qa.x, qa.y)));
+    const float2 e23 = __ffma2_rn(ak, make_float2(xa.z, xa.w), __ffma2_rn(bk, make_float2(ya.z, ya.w), make_float2(qa.z, qa.w)));
+    const float2 e45 = __ffma2_rn(ak, make_float2(xb.x, xb.y), __ffma2_rn(bk, make_float2(yb.x, yb.y), make_float2(qb.x, qb.y)));
+    const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
+    const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
+                          fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
+    track<S>(c, k, m, g);
+  }
+}
+
+// Pruned candidate sweep.  The 32*S sources of a pass are consecutive scan points, i.e. a short
+// piece of wall; their bounding circle is compared with the bounding circle of every group of
+// 8 targets.  Stage A evaluates the groups whose circles overlap the sources' circle; that
+// yields, per source, an upper bound of its nearest-neighbour distance.  Stage B evaluates
+// every remaining group whose circle could still hold a point within (that bound + the
+// ambiguity margin) of any source.  Every skipped group is PROVEN farther than best + margin
+// for every source of the pass, so the tracked best / runner-up / group are exactly what the
+// full sweep would have produced for the purposes of nn-resolution; on
+// unordered inputs every group overlaps and this degenerates to the full sweep.
+template <int S>
+__device__ __forceinline__ void warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
+                                                       const float (&sy)[S], const bool (&valid)[S],
+                                                       Candidates<S>& c) {
+  float a[S], b[S], ss[S];
+  float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    a[k] = -2.0f * sx[k]; b[k] = -2.0f * sy[k];
+    ss[k] = fmaf(sx[k], sx[k], sy[k] * sy[k]);
+    c.best[k] = CUDART_INF_F; c.second[k] = CUDART_INF_F; c.group[k] = 0;
+    if (valid[k]) {
+      x0 = fminf(x0, sx[k]); x1 = fmaxf(x1, sx[k]);
+      y0 = fminf(y0, sy[k]); y1 = fmaxf(y1, sy[k]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = fminf(x0, __shfl_xor_sync(kFull, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(kFull, x1, o));
+    y0 = fminf(y0, __shfl_xor_sync(kFull, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(kFull, y1, o));
+  }
+  const float ckx = 0.5f * (x0 + x1), cky = 0.5f * (y0 + y1);
+  const float wx = x1 - x0, wy = y1 - y0;
+  const float csk = fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(y0), fabsf(y1)));
+  // source circle radius (half diagonal of the box) + absolute slack for every FP32 rounding
+  // in the circle arithmetic (centres, radii, distances): ~(csk + tmax) * 2^-20
+  const float rk = 0.5f * sqrtf(fmaf(wx, wx, wy * wy)) * 1.000004f + (csk + t.tmax) * 9.5367432e-7f;
+  const int ngroups = t.ngroups;
+  const int words = (ngroups + 31) >> 5;
+  // ---- stage A: groups whose circle overlaps the sources' circle
+  for (int w = 0; w < words; ++w) {
+    const int g = (w << 5) + (threadIdx.x & 31);
+    bool hit = false;
+    if (g < ngroups) {
+      const float dx = t.gcx[g] - ckx, dy = t.gcy[g] - cky;
+      hit = sqrtf(fmaf(dx, dx, dy * dy)) * 0.999996f - rk - t.grad[g] <= 0.f;
+    }
+    unsigned mask = __ballot_sync(kFull, hit);
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      eval_group<S>(t, (w << 5) + bit, a, b, c);
+    }
+  }
+  // ---- upper bound of any source's NN distance^2, widened by the ambiguity margin
+  float ub2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < S; ++k)
+    if (valid[k]) ub2 = fmaxf(ub2, c.best[k] + ss[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ub2 = fmaxf(ub2, __shfl_xor_sync(kFull, ub2, o));
+  const float E2 = 9.5367432e-7f * t.tmax * (csk + t.tmax);            // as in is_ambiguous<true>
+  const float rho = 1.6868114e-7f * fmaxf(csk, t.tmax);
+  const float dB = sqrtf(fmaxf(ub2, 0.f) + E2) * 1.000001f;
+  const float margin = (E2 + 4.f * dB * rho + 2.f * rho * rho) * 1.000001f;
+  // (+ the FP32 rounding of |s|^2 itself, <= 4u * csk^2)                +inf if nothing hit
+  const float reach = sqrtf(fmaxf(ub2, 0.f) + E2 + 2.f * margin + csk * csk * 4.8e-7f) * 1.000004f;
+  // ---- stage B: the remaining groups that can still matter
+  for (int w = 0; w < words; ++w) {
+    const int g = (w << 5) + (threadIdx.x & 31);
+    bool hit = false;
+    if (g < ngroups) {
+      const float dx = t.gcx[g] - ckx, dy = t.gcy[g] - cky;
+      const float lb = sqrtf(fmaf(dx, dx, dy * dy)) * 0.999996f - rk - t.grad[g];
+      hit = lb > 0.f && lb <= reach;
+    }
+    unsigned mask = __ballot_sync(kFull, hit);
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      eval_group<S>(t, (w << 5) + bit, a, b, c);
     }
   }
 }
@@ -753,7 +887,7 @@ struct WarpCtx {
   int iters, inl;
 };
 
-template <int SC>
+template <int SC, bool PRUNE>
 __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
@@ -775,6 +909,9 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
   t.ft = t.fy + a.mcap;
   t.src = reinterpret_cast<double2*>(t.ft + a.mcap);       // 12*mcap bytes, mcap % 8 == 0
   WarpCtx* ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
+  t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + 160);
+  t.gcy = t.gcx + a.mcap / kGroup;
+  t.grad = t.gcy + a.mcap / kGroup;
 
   const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
   if (lane == 0) {
@@ -821,7 +958,14 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
           fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
         }
         Candidates<SC> c;
-        warp_candidates<SC>(t, fx, fy, c);
+        if (PRUNE) {
+          bool vld[SC];
+#pragma unroll
+          for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
+          warp_candidates_pruned<SC>(t, fx, fy, vld, c);
+        } else {
+          warp_candidates<SC>(t, fx, fy, c);
+        }
         // ---- exact decision in three straight-line phases so the SC matched-point loads
         //      (global, L1/L2) and the SC float64 sqrt chains overlap instead of serialising
         int j[SC];
@@ -1230,12 +1374,19 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
     LaunchShape ws = ls;
     ws.warps = 1;
     ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
+    if (env_int("B200ICP_PRUNE", 1) != 0) {
+      // pruned sweep: passes of 64 consecutive sources (2 per lane)
+      const int SP = 2;
+      args.ncap = (prob->src_pitch + 32 * SP - 1) / (32 * SP) * (32 * SP);
+      ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
+      return launch_pairs(icp_align_warp_kernel<2, true>, ws, args, st);
+    }
     switch (SC) {
-      case 2: return launch_pairs(icp_align_warp_kernel<2>, ws, args, st);
-      case 4: return launch_pairs(icp_align_warp_kernel<4>, ws, args, st);
-      case 6: return launch_pairs(icp_align_warp_kernel<6>, ws, args, st);
-      case 8: return launch_pairs(icp_align_warp_kernel<8>, ws, args, st);
-      default: return launch_pairs(icp_align_warp_kernel<12>, ws, args, st);
+      case 2: return launch_pairs(icp_align_warp_kernel<2, false>, ws, args, st);
+      case 4: return launch_pairs(icp_align_warp_kernel<4, false>, ws, args, st);
+      case 6: return launch_pairs(icp_align_warp_kernel<6, false>, ws, args, st);
+      case 8: return launch_pairs(icp_align_warp_kernel<8, false>, ws, args, st);
+      default: return launch_pairs(icp_align_warp_kernel<12, false>, ws, args, st);
     }
   }
   B200ICP_DISPATCH(icp_align_kernel)
