@@ -44,6 +44,7 @@ class Outputs(C.Structure):
         ("pose_total", C.c_void_p), ("pose_last", C.c_void_p), ("error", C.c_void_p),
         ("rmse", C.c_void_p), ("inliers", C.c_void_p), ("iterations", C.c_void_p),
         ("indices", C.c_void_p), ("src_final", C.c_void_p), ("index_history", C.c_void_p),
+        ("evaluated_pairs", C.c_void_p),
     ]
 
 

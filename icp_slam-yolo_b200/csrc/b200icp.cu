@@ -51,6 +51,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef B200ICP_WARP_MIN_BLOCKS
 #define B200ICP_WARP_MIN_BLOCKS 16
 #endif
+#ifndef B200ICP_EVAL_UNROLL2
+#define B200ICP_EVAL_UNROLL2 0
+#endif
 
 thread_local char g_last_error[512] = "";
 
@@ -301,21 +304,36 @@ __device__ __forceinline__ double dist2_f64(double sx, double sy, double2 t) {
 //             the FP32-rounded points sit within rho = 2.83u*max(cs,tmax) of the true
 //             ones -> margin = 2*8u*tmax*(cs+tmax) + 4*dB*rho + 2*rho^2 on (second - best),
 //             dB an upper bound of the best distance.            (Derivations: DESIGN.md)
+// Guard band of the expanded form in e-space, monotone in cs:  2*8u*tmax(cs+tmax) for the two
+// FFMA roundings + 4*dB*rho + 2*rho^2 for the FP32 rounding of the points themselves, with the
+// best distance bounded by dB <= sqrt(2)(cs+tmax) and rho = 2.83u*max(cs,tmax):
+//   margin <= 2^-20 (cs+tmax)(tmax + 1.2 max(cs,tmax))
+__device__ __forceinline__ float expanded_margin(float cs, float tmax) {
+  return 9.5367432e-7f * (cs + tmax) * fmaf(1.2f, fmaxf(cs, tmax), tmax);
+}
+
 template <bool EXPANDED>
 __device__ __forceinline__ bool is_ambiguous(float best, float second, float scx, float scy,
                                              float tmax) {
   const float cs = fmaxf(fabsf(scx), fabsf(scy));
-  if (EXPANDED) {
-    const float E2 = 9.5367432e-7f * tmax * (cs + tmax);                    // 2 * 8u * ...
-    const float rho = 1.6868114e-7f * fmaxf(cs, tmax);                      // 2.83 u
-    const float ss = fmaf(scx, scx, scy * scy);
-    const float dB = sqrtf(fmaxf(best + ss, 0.f) + E2) * 1.000001f;
-    const float margin = (E2 + 4.f * dB * rho + 2.f * rho * rho) * 1.000001f;
-    return (second - best) <= margin;        // near-equal floats subtract exactly
-  }
+  if (EXPANDED) return (second - best) <= expanded_margin(cs, tmax);   // near-equal floats subtract exactly
   const float guard = (cs + tmax) * 4.76837158e-7f;                         // 4*eta = 2^-21 (..)
   const float r = sqrtf(best) * 1.00000095f + guard;
   return second <= r * r * 1.00000024f;
+}
+
+// sqrt of a float64 in [~1e-30, ~1e30]: FP32 rsqrt seed + two Newton steps on the residual
+// (9 instructions instead of ~20 + a slow-path branch).  Faithfully rounded (<= 1 ulp), which is
+// far inside the 1e-9 relative error budget of the mean-distance bookkeeping.
+__device__ __forceinline__ double sqrt_f64_fast(double x) {
+  const float xf = (float)x;
+  if (!(xf > 1e-30f && xf < 1e30f)) return sqrt(x);          // zero, tiny, huge, NaN: library path
+  const double y = (double)rsqrtf(xf);
+  double g = x * y;
+  const double h = 0.5 * y;
+  g = fma(fma(-g, g, x), h, g);
+  g = fma(fma(-g, g, x), h, g);
+  return g;
 }
 
 // Re-decide every correspondence in float64.  Must be called by all lanes of the warp.
@@ -664,7 +682,9 @@ __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
   t.oy = sy / (double)t.m;
   float amax = 0.f;
   for (int j = lane; j < t.mcap; j += 32) {
-    float cx = 0.f, cy = 0.f, tt = CUDART_INF_F;
+    // sentinels: |t|^2 = +inf makes the expanded form +inf (no inf - inf: the coordinates stay
+    // finite), and 1e18 makes the direct-difference form ~2e36, finite and never the minimum
+    float cx = 1e18f, cy = 1e18f, tt = CUDART_INF_F;
     if (j < t.m) {
       const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
       cx = (float)(q.x - t.ox); cy = (float)(q.y - t.oy);
@@ -738,27 +758,69 @@ __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (
   }
 }
 
-// One group of 8 targets against the S sources of a lane (expanded form, packed FFMA2).
-template <int S>
-__device__ __forceinline__ void eval_group(const WarpTile& t, int g, const float (&a)[S],
-                                           const float (&b)[S], Candidates<S>& c) {
+// One group of 8 targets against the S sources of a lane (expanded form, packed FFMA2),
+// split into the shared-memory loads and the arithmetic so the candidate loop can fetch the
+// next group while the current one is being evaluated.
+struct GroupRegs {
+  float4 xa, xb, ya, yb, qa, qb;
+};
+
+__device__ __forceinline__ GroupRegs load_group(const WarpTile& t, int g) {
   const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
   const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
   const float4* __restrict__ q4 = reinterpret_cast<const float4*>(t.ft);
-  const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
-  const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
-  const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
+  GroupRegs r;
+  r.xa = x4[2 * g]; r.xb = x4[2 * g + 1];
+  r.ya = y4[2 * g]; r.yb = y4[2 * g + 1];
+  r.qa = q4[2 * g]; r.qb = q4[2 * g + 1];
+  return r;
+}
+
+template <int S>
+__device__ __forceinline__ void eval_group(const GroupRegs& r, int g, const float (&a)[S],
+                                           const float (&b)[S], Candidates<S>& c) {
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
-    const float2 e01 = __ffma2_rn(ak, make_float2(xa.x, xa.y), __ffma2_rn(bk, make_float2(ya.x, ya.y), make_float2(qa.x, qa.y)));
-    const float2 e23 = __ffma2_rn(ak, make_float2(xa.z, xa.w), __ffma2_rn(bk, make_float2(ya.z, ya.w), make_float2(qa.z, qa.w)));
-    const float2 e45 = __ffma2_rn(ak, make_float2(xb.x, xb.y), __ffma2_rn(bk, make_float2(yb.x, yb.y), make_float2(qb.x, qb.y)));
-    const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
+    const float2 e01 = __ffma2_rn(ak, make_float2(r.xa.x, r.xa.y), __ffma2_rn(bk, make_float2(r.ya.x, r.ya.y), make_float2(r.qa.x, r.qa.y)));
+    const float2 e23 = __ffma2_rn(ak, make_float2(r.xa.z, r.xa.w), __ffma2_rn(bk, make_float2(r.ya.z, r.ya.w), make_float2(r.qa.z, r.qa.w)));
+    const float2 e45 = __ffma2_rn(ak, make_float2(r.xb.x, r.xb.y), __ffma2_rn(bk, make_float2(r.yb.x, r.yb.y), make_float2(r.qb.x, r.qb.y)));
+    const float2 e67 = __ffma2_rn(ak, make_float2(r.xb.z, r.xb.w), __ffma2_rn(bk, make_float2(r.yb.z, r.yb.w), make_float2(r.qb.z, r.qb.w)));
     const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
                           fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
     track<S>(c, k, m, g);
   }
+}
+
+// Evaluate every group whose bit is set in `mask` (groups base_g + bit).
+template <int S>
+__device__ __forceinline__ void eval_mask(const WarpTile& t, unsigned mask, int base_g,
+                                          const float (&a)[S], const float (&b)[S],
+                                          Candidates<S>& c) {
+#if B200ICP_EVAL_UNROLL2
+  while (mask) {                     // two groups per trip: 12 loads in flight before the math
+    const int g0 = base_g + __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (mask) {
+      const int g1 = base_g + __ffs(mask) - 1;
+      mask &= mask - 1;
+      const GroupRegs r0 = load_group(t, g0);
+      const GroupRegs r1 = load_group(t, g1);
+      eval_group<S>(r0, g0, a, b, c);
+      eval_group<S>(r1, g1, a, b, c);
+    } else {
+      const GroupRegs r0 = load_group(t, g0);
+      eval_group<S>(r0, g0, a, b, c);
+    }
+  }
+#else
+  while (mask) {
+    const int g = base_g + __ffs(mask) - 1;
+    mask &= mask - 1;
+    const GroupRegs r = load_group(t, g);
+    eval_group<S>(r, g, a, b, c);
+  }
+#endif
 }
 
 // Pruned candidate sweep.  The 32*S sources of a pass are consecutive scan points, i.e. a short
@@ -771,9 +833,10 @@ __device__ __forceinline__ void eval_group(const WarpTile& t, int g, const float
 // full sweep would have produced for the purposes of nn-resolution; on
 // unordered inputs every group overlaps and this degenerates to the full sweep.
 template <int S>
-__device__ __forceinline__ void warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
-                                                       const float (&sy)[S], const bool (&valid)[S],
-                                                       Candidates<S>& c) {
+__device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
+                                                      const float (&sy)[S], const bool (&valid)[S],
+                                                      Candidates<S>& c) {
+  int evaluated = 0;            // groups swept in this pass (diagnostics)
   float a[S], b[S], ss[S];
   float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
 #pragma unroll
@@ -807,12 +870,9 @@ __device__ __forceinline__ void warp_candidates_pruned(const WarpTile& t, const 
       const float dx = t.gcx[g] - ckx, dy = t.gcy[g] - cky;
       hit = sqrtf(fmaf(dx, dx, dy * dy)) * 0.999996f - rk - t.grad[g] <= 0.f;
     }
-    unsigned mask = __ballot_sync(kFull, hit);
-    while (mask) {
-      const int bit = __ffs(mask) - 1;
-      mask &= mask - 1;
-      eval_group<S>(t, (w << 5) + bit, a, b, c);
-    }
+    const unsigned mask = __ballot_sync(kFull, hit);
+    evaluated += __popc(mask);
+    eval_mask<S>(t, mask, w << 5, a, b, c);
   }
   // ---- upper bound of any source's NN distance^2, widened by the ambiguity margin
   float ub2 = 0.f;
@@ -821,12 +881,10 @@ __device__ __forceinline__ void warp_candidates_pruned(const WarpTile& t, const 
     if (valid[k]) ub2 = fmaxf(ub2, c.best[k] + ss[k]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ub2 = fmaxf(ub2, __shfl_xor_sync(kFull, ub2, o));
-  const float E2 = 9.5367432e-7f * t.tmax * (csk + t.tmax);            // as in is_ambiguous<true>
-  const float rho = 1.6868114e-7f * fmaxf(csk, t.tmax);
-  const float dB = sqrtf(fmaxf(ub2, 0.f) + E2) * 1.000001f;
-  const float margin = (E2 + 4.f * dB * rho + 2.f * rho * rho) * 1.000001f;
-  // (+ the FP32 rounding of |s|^2 itself, <= 4u * csk^2)                +inf if nothing hit
-  const float reach = sqrtf(fmaxf(ub2, 0.f) + E2 + 2.f * margin + csk * csk * 4.8e-7f) * 1.000004f;
+  // slot-level margin >= every lane's is_ambiguous margin (monotone in cs); + the FP32 rounding
+  // of |s|^2 itself (<= 4u * csk^2).  +inf if stage A hit nothing.
+  const float margin = expanded_margin(csk, t.tmax);
+  const float reach = sqrtf(fmaxf(ub2, 0.f) + 3.f * margin + csk * csk * 4.8e-7f) * 1.000004f;
   // ---- stage B: the remaining groups that can still matter
   for (int w = 0; w < words; ++w) {
     const int g = (w << 5) + (threadIdx.x & 31);
@@ -836,13 +894,11 @@ __device__ __forceinline__ void warp_candidates_pruned(const WarpTile& t, const 
       const float lb = sqrtf(fmaf(dx, dx, dy * dy)) * 0.999996f - rk - t.grad[g];
       hit = lb > 0.f && lb <= reach;
     }
-    unsigned mask = __ballot_sync(kFull, hit);
-    while (mask) {
-      const int bit = __ffs(mask) - 1;
-      mask &= mask - 1;
-      eval_group<S>(t, (w << 5) + bit, a, b, c);
-    }
+    const unsigned mask = __ballot_sync(kFull, hit);
+    evaluated += __popc(mask);
+    eval_mask<S>(t, mask, w << 5, a, b, c);
   }
+  return evaluated;
 }
 
 // Inside the best group: FP32 direct-difference distances of its 8 targets, the 3-bit slot
@@ -857,13 +913,11 @@ __device__ __forceinline__ int in_group_argmin(const WarpTile& t, int g, float f
   const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
   const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
   const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-  const float* tt = t.ft + g * kGroup;
   unsigned best = 0x7f800000u, second = 0x7f800000u;       // +inf as ordered bit patterns
 #pragma unroll
   for (int u = 0; u < kGroup; ++u) {
     const float dx = fx - xs[u], dy = fy - ys[u];
-    float d = fmaf(dy, dy, dx * dx);
-    if (u > 0 && tt[u] == CUDART_INF_F) d = CUDART_INF_F;   // sentinel slots never win
+    const float d = fmaf(dy, dy, dx * dx);                   // sentinel slots: ~2e36, never win
     const unsigned key = (__float_as_uint(d) & ~7u) | (unsigned)u;   // d >= 0: bits are ordered
     second = min(second, max(best, key));
     best = min(best, key);
@@ -929,6 +983,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
   }
   __syncwarp();
   int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
+  long long evals = 0;          // pair evaluations executed by the sweep (padded targets included)
 
   if (ran) {
     warp_stage_targets(t, lane);
@@ -962,9 +1017,11 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
           bool vld[SC];
 #pragma unroll
           for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
-          warp_candidates_pruned<SC>(t, fx, fy, vld, c);
+          const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c);
+          evals += (long long)groups * kGroup * min(32 * SC, n - base);
         } else {
           warp_candidates<SC>(t, fx, fy, c);
+          evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
         }
         // ---- exact decision in three straight-line phases so the SC matched-point loads
         //      (global, L1/L2) and the SC float64 sqrt chains overlap instead of serialising
@@ -1024,7 +1081,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
             const double2 s = t.src[i];
             const double2 b = bm[k];
             const double d2 = dist2_f64(s.x, s.y, b);
-            const double dist = sqrt(d2);
+            const double dist = sqrt_f64_fast(d2);
             if (!use_gate || dist < gate) {
               const double ax = s.x - t.ox, ay = s.y - t.oy;
               const double qx = b.x - t.ox, qy = b.y - t.oy;
@@ -1102,6 +1159,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
     if (out.rmse) out.rmse[p] = sqrt(ctx->mean_d2);
     if (out.inliers) out.inliers[p] = ctx->inl;
     out.iterations[p] = iters;
+    if (out.evaluated_pairs) out.evaluated_pairs[p] = evals;
   }
   if (idx_out) {
     for (int i = lane; i < pr.src_pitch; i += 32)
@@ -1376,10 +1434,16 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
     ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
     if (env_int("B200ICP_PRUNE", 1) != 0) {
       // pruned sweep: passes of 64 consecutive sources (2 per lane)
-      const int SP = 2;
+      int SP = env_int("B200ICP_PRUNE_S", 2);
+      if (SP < 1 || SP > 4) SP = 2;
       args.ncap = (prob->src_pitch + 32 * SP - 1) / (32 * SP) * (32 * SP);
       ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
-      return launch_pairs(icp_align_warp_kernel<2, true>, ws, args, st);
+      switch (SP) {
+        case 1: return launch_pairs(icp_align_warp_kernel<1, true>, ws, args, st);
+        case 2: return launch_pairs(icp_align_warp_kernel<2, true>, ws, args, st);
+        case 3: return launch_pairs(icp_align_warp_kernel<3, true>, ws, args, st);
+        default: return launch_pairs(icp_align_warp_kernel<4, true>, ws, args, st);
+      }
     }
     switch (SC) {
       case 2: return launch_pairs(icp_align_warp_kernel<2, false>, ws, args, st);

@@ -104,6 +104,7 @@ class AlignResult:
     indices: Optional[torch.Tensor] = None
     src_final: Optional[torch.Tensor] = None
     index_history: Optional[torch.Tensor] = None
+    evaluated_pairs: Optional[torch.Tensor] = None   # int64: pair-evals the sweep executed
 
     def rotation(self, which: str = "total") -> torch.Tensor:
         p = self.pose_total if which == "total" else self.pose_last
@@ -185,7 +186,8 @@ def nn_search(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
 
 
 def alloc_outputs(n_pairs: int, src_pitch: int, device, *, max_iterations: int = 0,
-                  want_indices=False, want_src=False, want_history=False) -> AlignResult:
+                  want_indices=False, want_src=False, want_history=False,
+                  want_stats=False) -> AlignResult:
     f64 = dict(dtype=torch.float64, device=device)
     i32 = dict(dtype=torch.int32, device=device)
     return AlignResult(
@@ -199,6 +201,7 @@ def alloc_outputs(n_pairs: int, src_pitch: int, device, *, max_iterations: int =
         src_final=torch.empty((n_pairs, src_pitch, 2), **f64) if want_src else None,
         index_history=(torch.full((n_pairs, max_iterations, src_pitch), -1, **i32)
                        if want_history else None),
+        evaluated_pairs=torch.zeros(n_pairs, dtype=torch.int64, device=device) if want_stats else None,
     )
 
 
@@ -207,7 +210,7 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
                 max_iterations: int = 20, tolerance: float = 1e-5,
                 init_pose: Optional[torch.Tensor] = None, max_corr_dist: Optional[float] = None,
                 want_indices: bool = False, want_src: bool = False, want_history: bool = False,
-                out: Optional[AlignResult] = None, stream=None) -> AlignResult:
+                want_stats: bool = False, out: Optional[AlignResult] = None, stream=None) -> AlignResult:
     """Run the whole ICP loop of every pair on the device (one kernel launch).
 
     Replaces ``icp(A, B, max_iterations, tolerance)`` (icp.py:28-53) for a batch:
@@ -219,7 +222,8 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     dev = src.points.device
     if out is None:
         out = alloc_outputs(b, src.pitch, dev, max_iterations=max_iterations,
-                            want_indices=want_indices, want_src=want_src, want_history=want_history)
+                            want_indices=want_indices, want_src=want_src, want_history=want_history,
+                            want_stats=want_stats)
     opt = _cabi.Options()
     opt.max_iterations = int(max_iterations)
     opt.tolerance = float(tolerance)
@@ -236,6 +240,7 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     o.indices = None if out.indices is None else out.indices.data_ptr()
     o.src_final = None if out.src_final is None else out.src_final.data_ptr()
     o.index_history = None if out.index_history is None else out.index_history.data_ptr()
+    o.evaluated_pairs = None if out.evaluated_pairs is None else out.evaluated_pairs.data_ptr()
     with torch.cuda.device(dev):
         rc = _cabi.lib().b200icp_align_batch(C.byref(pr), b, C.byref(opt), C.byref(o),
                                              _stream_ptr(stream))

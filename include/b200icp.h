@@ -105,6 +105,10 @@ typedef struct b200icp_outputs {
   int32_t* indices;     /* [n_pairs][src_pitch] correspondences of the last search       */
   double* src_final;    /* [n_pairs][src_pitch][2] transformed source (icp.py:45,53)     */
   int32_t* index_history; /* [n_pairs][max_iterations][src_pitch] (diagnostics/parity)   */
+  int64_t* evaluated_pairs; /* [n_pairs] source-target distance evaluations the candidate
+                               sweep actually executed (all iterations); the brute-force
+                               count is sum over iterations of n_src * n_tgt.  Diagnostics
+                               for the pruned sweep                      */
 } b200icp_outputs;
 
 /* ---- library ---------------------------------------------------------------- */
