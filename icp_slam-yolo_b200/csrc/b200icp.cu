@@ -832,6 +832,29 @@ __device__ __forceinline__ void eval_mask(const WarpTile& t, unsigned mask, int 
 // for every source of the pass, so the tracked best / runner-up / group are exactly what the
 // full sweep would have produced for the purposes of nn-resolution; on
 // unordered inputs every group overlaps and this degenerates to the full sweep.
+// Warp-wide min / max of a float through the integer REDUX unit (one instruction instead of a
+// five-step shuffle tree): floats are mapped to order-preserving unsigned keys first.
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+  const unsigned u = __float_as_uint(f);
+  return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(unsigned k) {
+  return __uint_as_float(k ^ (((k >> 31) - 1u) | 0x80000000u));
+}
+__device__ __forceinline__ float warp_min_f32(float f) {
+  return f32_unordered(__reduce_min_sync(kFull, f32_ordered(f)));
+}
+__device__ __forceinline__ float warp_max_f32(float f) {
+  return f32_unordered(__reduce_max_sync(kFull, f32_ordered(f)));
+}
+
+// squared distance from a point to an axis-aligned box (0 inside)
+__device__ __forceinline__ float box_dist2(float px, float py, float x0, float x1, float y0, float y1) {
+  const float dx = fmaxf(fmaxf(x0 - px, px - x1), 0.f);
+  const float dy = fmaxf(fmaxf(y0 - py, py - y1), 0.f);
+  return fmaf(dx, dx, dy * dy);
+}
+
 template <int S>
 __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
                                                       const float (&sy)[S], const bool (&valid)[S],
@@ -849,28 +872,29 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
       y0 = fminf(y0, sy[k]); y1 = fmaxf(y1, sy[k]);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    x0 = fminf(x0, __shfl_xor_sync(kFull, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(kFull, x1, o));
-    y0 = fminf(y0, __shfl_xor_sync(kFull, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(kFull, y1, o));
-  }
-  const float ckx = 0.5f * (x0 + x1), cky = 0.5f * (y0 + y1);
-  const float wx = x1 - x0, wy = y1 - y0;
+  // bounding box of the pass's sources
+  x0 = warp_min_f32(x0); x1 = warp_max_f32(x1);
+  y0 = warp_min_f32(y0); y1 = warp_max_f32(y1);
   const float csk = fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(y0), fabsf(y1)));
-  // source circle radius (half diagonal of the box) + absolute slack for every FP32 rounding
-  // in the circle arithmetic (centres, radii, distances): ~(csk + tmax) * 2^-20
-  const float rk = 0.5f * sqrtf(fmaf(wx, wx, wy * wy)) * 1.000004f + (csk + t.tmax) * 9.5367432e-7f;
+  // absolute slack for every FP32 rounding in the bound arithmetic: ~(csk + tmax) * 2^-20
+  const float slack = (csk + t.tmax) * 9.5367432e-7f;
   const int ngroups = t.ngroups;
   const int words = (ngroups + 31) >> 5;
-  // ---- stage A: groups whose circle overlaps the sources' circle
+  const int lane = threadIdx.x & 31;
+  // A group can hold a point within distance R of some source only if its circle (centre c,
+  // radius rho) comes within R of the sources' box:  box_dist(c) <= R + rho (+ slack).
+  // ---- stage A: R = 0, the groups whose circle touches the box
+  float d2w0 = CUDART_INF_F, d2w1 = CUDART_INF_F, rw0 = 0.f, rw1 = 0.f;   // words 0/1 cached
   for (int w = 0; w < words; ++w) {
-    const int g = (w << 5) + (threadIdx.x & 31);
-    bool hit = false;
+    const int g = (w << 5) + lane;
+    float d2 = CUDART_INF_F, rr = 0.f;
     if (g < ngroups) {
-      const float dx = t.gcx[g] - ckx, dy = t.gcy[g] - cky;
-      hit = sqrtf(fmaf(dx, dx, dy * dy)) * 0.999996f - rk - t.grad[g] <= 0.f;
+      d2 = box_dist2(t.gcx[g], t.gcy[g], x0, x1, y0, y1) * 0.999996f;
+      rr = t.grad[g] + slack;
     }
-    const unsigned mask = __ballot_sync(kFull, hit);
+    if (w == 0) { d2w0 = d2; rw0 = rr; }
+    if (w == 1) { d2w1 = d2; rw1 = rr; }
+    const unsigned mask = __ballot_sync(kFull, d2 <= rr * rr);
     evaluated += __popc(mask);
     eval_mask<S>(t, mask, w << 5, a, b, c);
   }
@@ -879,22 +903,26 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
 #pragma unroll
   for (int k = 0; k < S; ++k)
     if (valid[k]) ub2 = fmaxf(ub2, c.best[k] + ss[k]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ub2 = fmaxf(ub2, __shfl_xor_sync(kFull, ub2, o));
+  ub2 = warp_max_f32(ub2);
   // slot-level margin >= every lane's is_ambiguous margin (monotone in cs); + the FP32 rounding
   // of |s|^2 itself (<= 4u * csk^2).  +inf if stage A hit nothing.
   const float margin = expanded_margin(csk, t.tmax);
   const float reach = sqrtf(fmaxf(ub2, 0.f) + 3.f * margin + csk * csk * 4.8e-7f) * 1.000004f;
   // ---- stage B: the remaining groups that can still matter
   for (int w = 0; w < words; ++w) {
-    const int g = (w << 5) + (threadIdx.x & 31);
-    bool hit = false;
-    if (g < ngroups) {
-      const float dx = t.gcx[g] - ckx, dy = t.gcy[g] - cky;
-      const float lb = sqrtf(fmaf(dx, dx, dy * dy)) * 0.999996f - rk - t.grad[g];
-      hit = lb > 0.f && lb <= reach;
+    float d2, rr;
+    if (w == 0) { d2 = d2w0; rr = rw0; }
+    else if (w == 1) { d2 = d2w1; rr = rw1; }
+    else {
+      const int g = (w << 5) + lane;
+      d2 = CUDART_INF_F; rr = 0.f;
+      if (g < ngroups) {
+        d2 = box_dist2(t.gcx[g], t.gcy[g], x0, x1, y0, y1) * 0.999996f;
+        rr = t.grad[g] + slack;
+      }
     }
-    const unsigned mask = __ballot_sync(kFull, hit);
+    const float far = rr + reach;                          // +inf when stage A hit nothing
+    const unsigned mask = __ballot_sync(kFull, (w << 5) + lane < ngroups && d2 > rr * rr && d2 <= far * far);
     evaluated += __popc(mask);
     eval_mask<S>(t, mask, w << 5, a, b, c);
   }
