@@ -150,7 +150,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -266,7 +266,6 @@ def run_b200(args):
     barrier()
     total_ms = max_over_ranks(t_all0.elapsed_time(t_all1))
     kernel_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs]))     # per-launch duration
-    clocks = sampler.stop() if rank == 0 else None
     assert bool(torch.all(out.iterations == ITERS)), "forced-iteration run did not run 30 iterations"
     # untimed diagnostic launch: how many pair evaluations did the (exactly pruned) sweep execute?
     stats = m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, want_stats=True)
@@ -298,6 +297,7 @@ def run_b200(args):
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "launches_per_step": pipe.launches,
                "api": "icp_slam_yolo_b200.registration.HostPipeline.run (16 chunks, copy/compute overlap)"}
 
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions
     if rank != 0:
         return
 
