@@ -7,7 +7,8 @@
 // with *per-chunk* origins so the FP32 error band stays ~1e-5 mm even for maps that span
 // tens of metres:
 //   s2m_prepare_kernel   chunk centroids, chunk-centred float32 SoA copy of the shard
-//   s2m_sweep_kernel     per (source, target segment): upper bound of the best distance,
+//   s2m_bound / s2m_cull per tile of 512 scan points, the ordered list of chunks that can matter
+//   s2m_sweep_kernel     per (source, 8 listed chunks): upper bound of the best distance,
 //                        lower bounds of the best and of the runner-up group, best group
 //   s2m_resolve_kernel   merge segments, FP32 in-group argmin, exact float64 distance of the
 //                        winner; sources whose runner-up may beat the winner go to a list
@@ -151,19 +152,117 @@ __global__ void __launch_bounds__(256) s2m_prepare_kernel(const void* points, in
 }
 
 // ------------------------------------------------------------------------------------------
+// culling: which chunks can matter for a tile of 512 consecutive scan points?
+//   bound: ub_i = min_c (|s_i - o_c| + r_c) is an upper bound of point i's NN distance (some map
+//          point of chunk c lies within r_c of its origin o_c); one cheap pass over the chunk
+//          table (n x n_chunks centre distances, ~0.1 % of the full sweep).
+//   cull : chunk c is kept for tile T iff dist(o_c, box(T)) - r_c <= max_{i in T} ub_i (+ slack).
+//          Every point of a culled chunk is farther from every point of the tile than that
+//          point's nearest neighbour, so it can be neither the winner nor a tie: results are
+//          identical to the full sweep.  Kept chunks are written as an ordered list per tile.
+// ------------------------------------------------------------------------------------------
+constexpr int kSegChunks = 8;         // listed chunks per sweep CTA
+constexpr float kSqrt2Up = 1.4142137f;
+
+__global__ void __launch_bounds__(128) s2m_bound_kernel(const double* __restrict__ origin,
+                                                        const float* __restrict__ radius, int n_chunks,
+                                                        const double* __restrict__ src64, int n,
+                                                        float* __restrict__ ub,
+                                                        const b200icp_s2m_state* __restrict__ state) {
+  if (state->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sx = src64[2 * i], sy = src64[2 * i + 1];
+  float best = CUDART_INF_F;
+  for (int c = 0; c < n_chunks; ++c) {
+    const double2 o = __ldg(reinterpret_cast<const double2*>(origin) + c);
+    const float dx = (float)(sx - o.x), dy = (float)(sy - o.y);
+    best = fminf(best, sqrtf(fmaf(dx, dx, dy * dy)) + __ldg(radius + c) * kSqrt2Up);
+  }
+  ub[i] = best * 1.000002f + 1e-6f;
+}
+
+__global__ void __launch_bounds__(256) s2m_cull_kernel(const double* __restrict__ origin,
+                                                       const float* __restrict__ radius, int n_chunks,
+                                                       const double* __restrict__ src64, int n,
+                                                       const float* __restrict__ ub,
+                                                       int32_t* __restrict__ tile_count,
+                                                       int32_t* __restrict__ tile_list,
+                                                       const b200icp_s2m_state* __restrict__ state) {
+  __shared__ double sbox[8][4];
+  __shared__ float sreach[8];
+  __shared__ int wcount[8];
+  __shared__ int base;
+  if (state->done) return;
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double x0 = CUDART_INF, x1 = -CUDART_INF, y0 = CUDART_INF, y1 = -CUDART_INF;
+  float reach = 0.f;
+  for (int k = tid; k < kSrcPerCta; k += blockDim.x) {
+    const int i = tile * kSrcPerCta + k;
+    if (i < n) {
+      const double sx = src64[2 * i], sy = src64[2 * i + 1];
+      x0 = fmin(x0, sx); x1 = fmax(x1, sx); y0 = fmin(y0, sy); y1 = fmax(y1, sy);
+      reach = fmaxf(reach, ub[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = fmin(x0, __shfl_xor_sync(kFull, x0, o)); x1 = fmax(x1, __shfl_xor_sync(kFull, x1, o));
+    y0 = fmin(y0, __shfl_xor_sync(kFull, y0, o)); y1 = fmax(y1, __shfl_xor_sync(kFull, y1, o));
+    reach = fmaxf(reach, __shfl_xor_sync(kFull, reach, o));
+  }
+  if (lane == 0) { sbox[warp][0] = x0; sbox[warp][1] = x1; sbox[warp][2] = y0; sbox[warp][3] = y1; sreach[warp] = reach; }
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    x0 = fmin(x0, sbox[w][0]); x1 = fmax(x1, sbox[w][1]);
+    y0 = fmin(y0, sbox[w][2]); y1 = fmax(y1, sbox[w][3]);
+    reach = fmaxf(reach, sreach[w]);
+  }
+  const double lim = (double)reach * 1.000001 + 1e-3;        // slack: cull arithmetic is float64
+  int32_t* list = tile_list + (int64_t)tile * n_chunks;
+  for (int c0 = 0; c0 < n_chunks; c0 += blockDim.x) {
+    const int c = c0 + tid;
+    bool keep = false;
+    if (c < n_chunks) {
+      const double2 o = __ldg(reinterpret_cast<const double2*>(origin) + c);
+      const double dx = fmax(fmax(x0 - o.x, o.x - x1), 0.0), dy = fmax(fmax(y0 - o.y, o.y - y1), 0.0);
+      keep = sqrt(dx * dx + dy * dy) - (double)(radius[c] * kSqrt2Up) <= lim;
+    }
+    const unsigned ballot = __ballot_sync(kFull, keep);
+    if (lane == 0) wcount[warp] = __popc(ballot);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += wcount[w];
+    if (keep) list[off + __popc(ballot & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += wcount[w];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) tile_count[tile] = base;
+}
+
+// ------------------------------------------------------------------------------------------
 // sweep: FP32 direct-difference search of a segment of chunks for 512 source points
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSweepThreads) s2m_sweep_kernel(
     const float* __restrict__ cx, const float* __restrict__ cy, const double* __restrict__ origin,
-    const float* __restrict__ radius, int n_chunks, int chunks_per_seg,
-    const double* __restrict__ src64, int n, Partial* __restrict__ partials,
-    const b200icp_s2m_state* __restrict__ state) {
+    const float* __restrict__ radius, int n_chunks, const int32_t* __restrict__ tile_count,
+    const int32_t* __restrict__ tile_list, const double* __restrict__ src64, int n,
+    Partial* __restrict__ partials, const b200icp_s2m_state* __restrict__ state) {
   __shared__ __align__(128) float buf[2][2][kChunk];     // [stage][x|y][point]
   __shared__ __align__(8) uint64_t bars[2];
   if (state->done) return;
   const int tid = threadIdx.x;
-  const int seg = blockIdx.x, tile = blockIdx.y;
-  const int c0 = seg * chunks_per_seg, c1 = min(n_chunks, c0 + chunks_per_seg);
+  const int item = blockIdx.x, tile = blockIdx.y;
+  const int kept = tile_count[tile];
+  const int c0 = item * kSegChunks, c1 = min(kept, c0 + kSegChunks);   // positions in the tile's list
+  if (c0 >= c1) return;
+  const int32_t* __restrict__ list = tile_list + (int64_t)tile * n_chunks;
 
   double sx[kSweepS], sy[kSweepS];
   float g_ub[kSweepS], g_lb1[kSweepS], g_lb2[kSweepS];
@@ -182,18 +281,21 @@ __global__ void __launch_bounds__(kSweepThreads) s2m_sweep_kernel(
   }
   __syncthreads();
   constexpr uint32_t kHalf = kChunk * sizeof(float);
-  if (tid == 0 && c0 < c1) {
+  if (tid == 0) {
+    const int64_t cc = list[c0];
     mbar_expect_tx(&bars[0], 2 * kHalf);
-    bulk_g2s(&buf[0][0][0], cx + (int64_t)c0 * kChunk, kHalf, &bars[0]);
-    bulk_g2s(&buf[0][1][0], cy + (int64_t)c0 * kChunk, kHalf, &bars[0]);
+    bulk_g2s(&buf[0][0][0], cx + cc * kChunk, kHalf, &bars[0]);
+    bulk_g2s(&buf[0][1][0], cy + cc * kChunk, kHalf, &bars[0]);
   }
-  for (int c = c0; c < c1; ++c) {
-    const int st = (c - c0) & 1;
-    const uint32_t phase = ((c - c0) >> 1) & 1;
-    if (tid == 0 && c + 1 < c1) {            // stage st^1 was released by the barrier below
+  for (int pos = c0; pos < c1; ++pos) {
+    const int c = list[pos];                  // the chunk swept in this trip
+    const int st = (pos - c0) & 1;
+    const uint32_t phase = ((pos - c0) >> 1) & 1;
+    if (tid == 0 && pos + 1 < c1) {          // stage st^1 was released by the barrier below
+      const int64_t cn = list[pos + 1];
       mbar_expect_tx(&bars[st ^ 1], 2 * kHalf);
-      bulk_g2s(&buf[st ^ 1][0][0], cx + (int64_t)(c + 1) * kChunk, kHalf, &bars[st ^ 1]);
-      bulk_g2s(&buf[st ^ 1][1][0], cy + (int64_t)(c + 1) * kChunk, kHalf, &bars[st ^ 1]);
+      bulk_g2s(&buf[st ^ 1][0][0], cx + cn * kChunk, kHalf, &bars[st ^ 1]);
+      bulk_g2s(&buf[st ^ 1][1][0], cy + cn * kChunk, kHalf, &bars[st ^ 1]);
     }
     const double ox = origin[2 * c], oy = origin[2 * c + 1];
     const float rc = radius[c];
@@ -251,7 +353,7 @@ __global__ void __launch_bounds__(kSweepThreads) s2m_sweep_kernel(
     if (i < n) {
       Partial p;
       p.ub = g_ub[k]; p.lb1 = g_lb1[k]; p.lb2 = g_lb2[k]; p.where = g_where[k];
-      partials[(int64_t)seg * n + i] = p;
+      partials[(int64_t)item * n + i] = p;
     }
   }
 }
@@ -262,15 +364,16 @@ __global__ void __launch_bounds__(kSweepThreads) s2m_sweep_kernel(
 __global__ void __launch_bounds__(128) s2m_resolve_kernel(
     const void* points, int dtype, int64_t m, int64_t global_offset, const float* __restrict__ cx,
     const float* __restrict__ cy, const double* __restrict__ origin, const float* __restrict__ radius,
-    const double* __restrict__ src64, int n, const Partial* __restrict__ partials, int n_seg,
-    b200icp_s2m_record* __restrict__ records, int32_t* __restrict__ amb_list,
+    const double* __restrict__ src64, int n, const Partial* __restrict__ partials,
+    const int32_t* __restrict__ tile_count, b200icp_s2m_record* __restrict__ records, int32_t* __restrict__ amb_list,
     int32_t* __restrict__ amb_count, const b200icp_s2m_state* __restrict__ state) {
   if (state->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g_ub = CUDART_INF_F, g_lb1 = CUDART_INF_F, g_lb2 = CUDART_INF_F;
   uint32_t where = 0;
-  for (int s = 0; s < n_seg; ++s) {
+  const int n_items = (tile_count[i / kSrcPerCta] + kSegChunks - 1) / kSegChunks;
+  for (int s = 0; s < n_items; ++s) {
     const Partial p = partials[(int64_t)s * n + i];
     merge_partial(g_ub, g_lb1, g_lb2, where, p.ub, p.lb1, p.lb2, p.where);
   }
@@ -524,13 +627,26 @@ int cuda_check(const char* what) {
   return B200ICP_ERR_CUDA;
 }
 
-int segments_for(int n_chunks, int n, int sms) {
-  const int tiles = (n + kSrcPerCta - 1) / kSrcPerCta;
-  int want = (4 * sms + tiles - 1) / tiles;            // ~4 CTAs per SM in total
-  if (want < 1) want = 1;
-  if (want > n_chunks) want = n_chunks;
-  const int per = (n_chunks + want - 1) / want;
-  return (n_chunks + per - 1) / per;
+struct Workspace {        // byte offsets inside the caller's workspace
+  int64_t amb_list, ub, tile_count, tile_list, partials, exact, total;
+  int n_items, tiles;
+};
+
+Workspace layout_workspace(int n, int64_t m) {
+  auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+  Workspace w;
+  const int64_t n_chunks = (m + kChunk - 1) / kChunk;
+  w.tiles = (n + kSrcPerCta - 1) / kSrcPerCta;
+  w.n_items = (int)((n_chunks + kSegChunks - 1) / kSegChunks);
+  int64_t off = 256;                                         // [0]: ambiguous-source counter
+  w.amb_list = off;   off += up((int64_t)n * 4);
+  w.ub = off;         off += up((int64_t)n * 4);
+  w.tile_count = off; off += up((int64_t)w.tiles * 4);
+  w.tile_list = off;  off += up((int64_t)w.tiles * n_chunks * 4);
+  w.partials = off;   off += up((int64_t)w.n_items * n * (int64_t)sizeof(Partial));
+  w.exact = off;      off += up((int64_t)n * kExactParts * (int64_t)sizeof(ExactPartial));
+  w.total = off;
+  return w;
 }
 
 }  // namespace
@@ -541,14 +657,7 @@ int b200icp_s2m_chunk(void) { return kChunk; }
 
 int64_t b200icp_s2m_workspace_bytes(int32_t n_scan, int64_t m) {
   if (n_scan < 1 || m < 1) return -1;
-  const int64_t n_chunks = (m + kChunk - 1) / kChunk;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms < 1) sms = 148;
-  const int64_t n_seg = segments_for((int)n_chunks, n_scan, sms);
-  const int64_t list_bytes = ((int64_t)n_scan * 4 + 64 + 127) / 128 * 128;
-  return list_bytes + n_seg * (int64_t)n_scan * (int64_t)sizeof(Partial) +
-         (int64_t)n_scan * kExactParts * (int64_t)sizeof(ExactPartial);
+  return layout_workspace(n_scan, m).total;
 }
 
 int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream) {
@@ -581,33 +690,37 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int3
     return fail("s2m_search: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
   if (workspace_bytes < b200icp_s2m_workspace_bytes(n, shard->m))
     return fail("s2m_search: workspace too small", B200ICP_ERR_INVALID_ARGUMENT);
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-    return fail("s2m_search: no CUDA device", B200ICP_ERR_NO_DEVICE);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n_chunks = (int)((shard->m + kChunk - 1) / kChunk);
-  const int n_seg = segments_for(n_chunks, n, sms);
-  const int per = (n_chunks + n_seg - 1) / n_seg;
-  const int tiles = (n + kSrcPerCta - 1) / kSrcPerCta;
-  // workspace: [ambiguous count (64 B)] [ambiguous list n x int32, padded] [partials]
-  int32_t* amb_count = reinterpret_cast<int32_t*>(workspace);
-  int32_t* amb_list = amb_count + 16;
-  const int64_t list_bytes = ((int64_t)n * 4 + 64 + 127) / 128 * 128;
-  Partial* partials = reinterpret_cast<Partial*>(reinterpret_cast<unsigned char*>(workspace) + list_bytes);
+  const Workspace w = layout_workspace(n, shard->m);
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  int32_t* amb_count = reinterpret_cast<int32_t*>(base);
+  int32_t* amb_list = reinterpret_cast<int32_t*>(base + w.amb_list);
+  float* ub = reinterpret_cast<float*>(base + w.ub);
+  int32_t* tile_count = reinterpret_cast<int32_t*>(base + w.tile_count);
+  int32_t* tile_list = reinterpret_cast<int32_t*>(base + w.tile_list);
+  Partial* partials = reinterpret_cast<Partial*>(base + w.partials);
   if (cudaMemsetAsync(amb_count, 0, 64, st) != cudaSuccess) return cuda_check("cudaMemsetAsync");
-  s2m_sweep_kernel<<<dim3(n_seg, tiles), kSweepThreads, 0, st>>>(
-      shard->cx, shard->cy, shard->chunk_origin, shard->chunk_radius, n_chunks, per, src64, n,
-      partials, state);
-  int rc = cuda_check("s2m_sweep_kernel");
+  s2m_bound_kernel<<<(n + 127) / 128, 128, 0, st>>>(shard->chunk_origin, shard->chunk_radius, n_chunks,
+                                                   src64, n, ub, state);
+  int rc = cuda_check("s2m_bound_kernel");
+  if (rc) return rc;
+  s2m_cull_kernel<<<w.tiles, 256, 0, st>>>(shard->chunk_origin, shard->chunk_radius, n_chunks, src64, n,
+                                          ub, tile_count, tile_list, state);
+  rc = cuda_check("s2m_cull_kernel");
+  if (rc) return rc;
+  s2m_sweep_kernel<<<dim3(w.n_items, w.tiles), kSweepThreads, 0, st>>>(
+      shard->cx, shard->cy, shard->chunk_origin, shard->chunk_radius, n_chunks, tile_count, tile_list,
+      src64, n, partials, state);
+  rc = cuda_check("s2m_sweep_kernel");
   if (rc) return rc;
   s2m_resolve_kernel<<<(n + 127) / 128, 128, 0, st>>>(
       shard->points, shard->dtype, shard->m, shard->global_offset, shard->cx, shard->cy,
-      shard->chunk_origin, shard->chunk_radius, src64, n, partials, n_seg, records, amb_list,
+      shard->chunk_origin, shard->chunk_radius, src64, n, partials, tile_count, records, amb_list,
       amb_count, state);
   rc = cuda_check("s2m_resolve_kernel");
   if (rc) return rc;
-  ExactPartial* exact_partials = reinterpret_cast<ExactPartial*>(partials + (int64_t)n_seg * n);
+  ExactPartial* exact_partials = reinterpret_cast<ExactPartial*>(base + w.exact);
   s2m_exact_scan_kernel<<<dim3(kExactParts, kExactRows), 256, 0, st>>>(
       shard->points, shard->dtype, shard->m, src64, amb_list, amb_count, exact_partials, state);
   rc = cuda_check("s2m_exact_scan_kernel");

@@ -102,7 +102,7 @@ class ScanToMap:
                                        _ptr(self.records), _ptr(self.workspace),
                                        self.workspace.numel(), _ptr(self.state), _stream_ptr(stream))
         _cabi.check(rc, "b200icp_s2m_search")
-        self.launches += 4
+        self.launches += 6
 
     def run(self, scan: torch.Tensor, *, max_iterations: int = 20, tolerance: float = 1e-5,
             init_pose=None, max_corr_dist: Optional[float] = None, sync: bool = True):
