@@ -164,22 +164,35 @@ __global__ void __launch_bounds__(256) s2m_prepare_kernel(const void* points, in
 constexpr int kSegChunks = 8;         // listed chunks per sweep CTA
 constexpr float kSqrt2Up = 1.4142137f;
 
+constexpr int kBoundChunks = 256;     // chunk origins staged per CTA of the bound kernel
+
+// grid (source blocks, chunk parts): every CTA stages kBoundChunks chunk origins in shared memory
+// and folds them into ub[] with an atomic min on the (non-negative) float bit patterns.
+// ub[] must be pre-set to a huge value (0x7f7f7f7f bytes).  Rounded up by the reader.
 __global__ void __launch_bounds__(128) s2m_bound_kernel(const double* __restrict__ origin,
                                                         const float* __restrict__ radius, int n_chunks,
                                                         const double* __restrict__ src64, int n,
                                                         float* __restrict__ ub,
                                                         const b200icp_s2m_state* __restrict__ state) {
+  __shared__ double sox[kBoundChunks], soy[kBoundChunks];
+  __shared__ float srad[kBoundChunks];
   if (state->done) return;
+  const int c0 = blockIdx.y * kBoundChunks, cnt = min(kBoundChunks, n_chunks - c0);
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+    sox[k] = origin[2 * (c0 + k)]; soy[k] = origin[2 * (c0 + k) + 1];
+    srad[k] = radius[c0 + k] * kSqrt2Up;
+  }
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double sx = src64[2 * i], sy = src64[2 * i + 1];
   float best = CUDART_INF_F;
-  for (int c = 0; c < n_chunks; ++c) {
-    const double2 o = __ldg(reinterpret_cast<const double2*>(origin) + c);
-    const float dx = (float)(sx - o.x), dy = (float)(sy - o.y);
-    best = fminf(best, sqrtf(fmaf(dx, dx, dy * dy)) + __ldg(radius + c) * kSqrt2Up);
+#pragma unroll 4
+  for (int k = 0; k < cnt; ++k) {
+    const float dx = (float)(sx - sox[k]), dy = (float)(sy - soy[k]);
+    best = fminf(best, sqrtf(fmaf(dx, dx, dy * dy)) + srad[k]);
   }
-  ub[i] = best * 1.000002f + 1e-6f;
+  atomicMin(reinterpret_cast<unsigned*>(ub) + i, __float_as_uint(best));
 }
 
 __global__ void __launch_bounds__(256) s2m_cull_kernel(const double* __restrict__ origin,
@@ -202,7 +215,7 @@ __global__ void __launch_bounds__(256) s2m_cull_kernel(const double* __restrict_
     if (i < n) {
       const double sx = src64[2 * i], sy = src64[2 * i + 1];
       x0 = fmin(x0, sx); x1 = fmax(x1, sx); y0 = fmin(y0, sy); y1 = fmax(y1, sy);
-      reach = fmaxf(reach, ub[i]);
+      reach = fmaxf(reach, ub[i] * 1.000002f + 1e-6f);     // ub holds the un-rounded minimum
     }
   }
 #pragma unroll
@@ -701,8 +714,9 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int3
   int32_t* tile_list = reinterpret_cast<int32_t*>(base + w.tile_list);
   Partial* partials = reinterpret_cast<Partial*>(base + w.partials);
   if (cudaMemsetAsync(amb_count, 0, 64, st) != cudaSuccess) return cuda_check("cudaMemsetAsync");
-  s2m_bound_kernel<<<(n + 127) / 128, 128, 0, st>>>(shard->chunk_origin, shard->chunk_radius, n_chunks,
-                                                   src64, n, ub, state);
+  if (cudaMemsetAsync(ub, 0x7f, (size_t)n * 4, st) != cudaSuccess) return cuda_check("cudaMemsetAsync");
+  s2m_bound_kernel<<<dim3((n + 127) / 128, (n_chunks + kBoundChunks - 1) / kBoundChunks), 128, 0, st>>>(
+      shard->chunk_origin, shard->chunk_radius, n_chunks, src64, n, ub, state);
   int rc = cuda_check("s2m_bound_kernel");
   if (rc) return rc;
   s2m_cull_kernel<<<w.tiles, 256, 0, st>>>(shard->chunk_origin, shard->chunk_radius, n_chunks, src64, n,
