@@ -280,7 +280,8 @@ def run_b200(args):
     # ---- e2e: pinned host buffers -> chunked H2D || kernel || D2H, through HostPipeline
     e2e = None
     if not args.no_e2e:
-        pipe = m.registration.HostPipeline(P, N_POINTS, N_POINTS, dtype=torch.float32, chunks=16, device=dev)
+        n_chunks = int(os.environ.get("B200ICP_E2E_CHUNKS", "4"))
+        pipe = m.registration.HostPipeline(P, N_POINTS, N_POINTS, dtype=torch.float32, chunks=n_chunks, device=dev)
         for _ in range(2):
             pipe.run(h_src, h_tgt, max_iterations=ITERS, tolerance=-1.0)
         barrier()
@@ -295,7 +296,7 @@ def run_b200(args):
         h2d, d2h = pipe.bytes_per_run(ragged=False)
         e2e = {"value": world * P / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "launches_per_step": pipe.launches,
-               "api": "icp_slam_yolo_b200.registration.HostPipeline.run (16 chunks, copy/compute overlap)"}
+               "api": "icp_slam_yolo_b200.registration.HostPipeline.run (%d chunks, copy/compute overlap)" % n_chunks}
 
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions
     if rank != 0:
@@ -322,7 +323,10 @@ def run_b200(args):
         "roofline": {"bound": "fp32", "kernel": "icp_align_warp_kernel<2,prune>", "achieved": achieved_tflops,
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                      "peak_source": "b200icp_ffma_probe measured live (dependent-FFMA chains, all SMs)",
-                     "algorithmic_flop_per_launch": flops, "kernel_ms": kernel_ms, "traffic": None,
+                     "algorithmic_flop_per_launch": flops, "kernel_ms": kernel_ms,
+                     "traffic": 389971968 if P == 65536 else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                       "capture profiles/r1f_align_pruned_ncu_details.txt (algorithmic: 380.6 MB)",
                      "executed_pair_eval_fraction": executed / (P * PAIR_EVALS_PER_ALIGNMENT),
                      "executed_tflops": executed * FLOP_PER_PAIR_EVAL / (kernel_ms * 1e-3) / 1e12,
                      "note": "achieved = brute-force-equivalent work (SURVEY.md 8d: N_src x N_tgt x iterations x 5 "
@@ -558,7 +562,11 @@ def run_scan2map(args):
         "roofline": {"bound": "fp32", "kernel": "s2m_sweep_kernel (+ resolve/exact)",
                      "achieved": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12 / fp32_peak,
-                     "kernel_ms": search_ms, "traffic": None},
+                     "kernel_ms": search_ms, "traffic": None,
+                     "note": "achieved = brute-force-equivalent work (N_scan x M_shard x 5 FLOP per search) / time of "
+                             "one b200icp_s2m_search (bound + cull + sweep + resolve + exact kernels).  Chunks that are "
+                             "provably out of reach of a 512-point tile are culled (identical results), so frac can "
+                             "exceed 1: it is not an FP32-pipe utilisation."},
     }
     print(json.dumps(line), flush=True)
 

@@ -294,7 +294,7 @@ class HostPipeline:
     """
 
     def __init__(self, n_pairs: int, src_pitch: int, tgt_pitch: int, dtype=torch.float32,
-                 chunks: int = 8, device="cuda"):
+                 chunks: int = 4, device="cuda"):
         self.n_pairs, self.src_pitch, self.tgt_pitch = int(n_pairs), int(src_pitch), int(tgt_pitch)
         self.device = torch.device(device)
         self.chunk = max(1, -(-self.n_pairs // max(1, chunks)))
