@@ -1263,6 +1263,84 @@ __global__ void __launch_bounds__(256) polar_to_cartesian_kernel(
 }
 
 // ------------------------------------------------------------------------------------
+// kernels: order-preserving point selection (the steps either side of registration in the
+// SLAM loop: local-map radius crop, duc/ICP_LIDAR/mainn.py:300-303; dynamic-point removal by
+// NN distance, duc/ICP_LIDAR/process.py:75-84).  count -> exclusive scan -> scatter.
+// ------------------------------------------------------------------------------------
+constexpr int kSelBlock = 1024;      // points per CTA (256 threads x 4)
+
+__device__ __forceinline__ bool select_keep(const void* points, int dtype, int64_t i, int mode,
+                                            const double* key, double cx, double cy, double thr) {
+  if (mode == 0) return key[i] < thr;
+  const double2 q = load_point(points, dtype, i);
+  const double dx = q.x - cx, dy = q.y - cy;
+  return dx * dx + dy * dy < thr;                       // mainn.py:302  distances_sq < R^2
+}
+
+__global__ void __launch_bounds__(256) select_count_kernel(const void* points, int dtype, int64_t n,
+                                                           int mode, const double* key, double cx,
+                                                           double cy, double thr, int64_t* block_counts) {
+  __shared__ int wc[8];
+  const int64_t base = (int64_t)blockIdx.x * kSelBlock;
+  int c = 0;
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = base + k * 256 + threadIdx.x;
+    if (i < n && select_keep(points, dtype, i, mode, key, cx, cy, thr)) ++c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+  if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += wc[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the per-block counts in place; total -> counts[n_blocks] and *count_out
+__global__ void select_scan_kernel(int64_t* counts, int64_t n_blocks, int64_t* count_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int64_t run = 0;
+    for (int64_t b = 0; b < n_blocks; ++b) { const int64_t c = counts[b]; counts[b] = run; run += c; }
+    counts[n_blocks] = run;
+    *count_out = run;
+  }
+}
+
+__global__ void __launch_bounds__(256) select_scatter_kernel(const void* points, int dtype, int64_t n,
+                                                             int mode, const double* key, double cx,
+                                                             double cy, double thr,
+                                                             const int64_t* block_offsets, void* out) {
+  __shared__ int wc[4][8];
+  const int64_t base = (int64_t)blockIdx.x * kSelBlock;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool keep[4];
+  unsigned ballots[4];
+  for (int k = 0; k < 4; ++k) {                         // point order: k-major, then thread
+    const int64_t i = base + k * 256 + threadIdx.x;
+    keep[k] = i < n && select_keep(points, dtype, i, mode, key, cx, cy, thr);
+    ballots[k] = __ballot_sync(kFull, keep[k]);
+    if (lane == 0) wc[k][warp] = __popc(ballots[k]);
+  }
+  __syncthreads();
+  int64_t off = block_offsets[blockIdx.x];
+  for (int k = 0; k < 4; ++k) {
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += wc[k][w];
+    if (keep[k]) {
+      const int64_t dst = off + before + __popc(ballots[k] & ((1u << lane) - 1u));
+      const int64_t i = base + k * 256 + threadIdx.x;
+      if (dtype == B200ICP_F64) reinterpret_cast<double2*>(out)[dst] = reinterpret_cast<const double2*>(points)[i];
+      else reinterpret_cast<float2*>(out)[dst] = reinterpret_cast<const float2*>(points)[i];
+    }
+    int row = 0;
+    for (int w = 0; w < 8; ++w) row += wc[k][w];
+    off += row;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // kernel: FP32 FFMA throughput probe (roofline denominator of the NN phase)
 // ------------------------------------------------------------------------------------
 constexpr int kProbeChains = 16;
@@ -1494,6 +1572,31 @@ int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_
       raw, raw_len, raw_pitch, xy_out, len_out, out_pitch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "polar_to_cartesian launch");
+  return B200ICP_OK;
+}
+
+int b200icp_select_points(const void* points, int32_t dtype, int64_t n, int32_t mode, const double* key,
+                          double cx, double cy, double threshold, void* out_points,
+                          int64_t* count_out, int64_t* scratch, void* stream) {
+  if (!points || !out_points || !count_out || !scratch || n < 0) { set_error("select_points: bad arguments"); return B200ICP_ERR_INVALID_ARGUMENT; }
+  if (dtype != B200ICP_F32 && dtype != B200ICP_F64) { set_error("select_points: bad dtype"); return B200ICP_ERR_INVALID_ARGUMENT; }
+  if (mode != 0 && mode != 1) { set_error("select_points: mode must be 0 (key) or 1 (radius)"); return B200ICP_ERR_INVALID_ARGUMENT; }
+  if (mode == 0 && !key) { set_error("select_points: mode 0 needs key"); return B200ICP_ERR_INVALID_ARGUMENT; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t blocks = (n + kSelBlock - 1) / kSelBlock;
+  if (blocks > 0) {
+    select_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(points, dtype, n, mode, key, cx, cy, threshold, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "select_count_kernel");
+  }
+  select_scan_kernel<<<1, 32, 0, st>>>(scratch, blocks, count_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "select_scan_kernel");
+  if (blocks > 0) {
+    select_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(points, dtype, n, mode, key, cx, cy, threshold, scratch, out_points);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "select_scatter_kernel");
+  }
   return B200ICP_OK;
 }
 

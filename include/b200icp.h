@@ -202,6 +202,19 @@ int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, d
                        int32_t* idx_out /*[n]|NULL*/, b200icp_s2m_state* state, void* stream);
 
 /*
+ * Order-preserving selection of points (the steps either side of registration in the SLAM loop).
+ *   mode 0: keep point i iff key[i] < threshold.  With key = squared NN distance to the previous
+ *           scan (b200icp_nn_batch / b200icp_s2m_search) and threshold = d^2 this replaces
+ *           remove_dynamic_points (duc/ICP_LIDAR/process.py:75-84: distances < distance_threshold).
+ *   mode 1: keep point i iff |p_i - (cx, cy)|^2 < threshold: the local-map radius crop
+ *           (duc/ICP_LIDAR/mainn.py:300-303: distances_sq < LOCAL_MAP_RADIUS_MM**2).
+ * out_points [n][2] (same dtype), count_out: device int64, scratch: device int64[ceil(n/1024)+1].
+ */
+int b200icp_select_points(const void* points, int32_t dtype, int64_t n, int32_t mode,
+                          const double* key, double cx, double cy, double threshold,
+                          void* out_points, int64_t* count_out, int64_t* scratch, void* stream);
+
+/*
  * FP32 FFMA throughput probe used as the roofline denominator of the NN phase
  * (MEASURED_PEAKS.json carries no FP32 figure).  Launches one kernel doing
  * `flop_out[0]` floating point operations (written to a HOST int64); the caller

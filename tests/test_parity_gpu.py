@@ -374,3 +374,30 @@ def test_align_variants_on_adversarial_shapes(b200, monkeypatch, variant, cart_s
             # decided by rounding noise (parity undefined) -- only the search is checked
             continue
         _check_pair(res, p, o, len(A[p]), rot=1e-9, trans=1e-5)
+
+
+def test_local_map_crop_and_dynamic_point_removal(b200, cart_scans):
+    """mainn.py:300-308 and process.py:75-84 on the device, order preserved."""
+    rng = np.random.default_rng(9)
+    big = rng.uniform(-20000, 20000, size=(50000, 2))
+    centre, radius = (1500.0, -700.0), 6000.0
+    got = b200.crop_local_map(torch.from_numpy(big).cuda(), centre, radius).cpu().numpy()
+    ref = big[np.sum((big - np.array(centre)) ** 2, axis=1) < radius ** 2]
+    assert np.array_equal(got, ref)
+    tiny = b200.crop_local_map(torch.from_numpy(big).cuda(), (1e6, 1e6), 10.0)
+    assert tiny.shape[0] == len(big)                               # < 50 survivors: whole map
+    cur, prev = cart_scans[500], cart_scans[499]
+    moved = cur.copy(); moved[::7] += 400.0                        # "dynamic" points
+    d, _ = orc.nn_kdtree(moved, prev)
+    for dt in (np.float64, np.float32):
+        got = b200.remove_dynamic_points(torch.from_numpy(moved.astype(dt)).cuda(),
+                                         torch.from_numpy(prev.astype(dt)).cuda(), 250.0).cpu().numpy()
+        dd, _ = orc.nn_kdtree(moved.astype(dt).astype(np.float64), prev.astype(dt).astype(np.float64))
+        assert np.array_equal(got, moved.astype(dt)[dd < 250.0])
+    assert 0 < np.sum(d < 250.0) < len(moved)
+    # large sets go through the sharded-map search
+    mp = orc.synth_map(30000, dtype=np.float64); sc = orc.synth_scan_for_map(2000, dtype=np.float64)
+    got = b200.remove_dynamic_points(torch.from_numpy(sc).cuda(), torch.from_numpy(mp).cuda(), 30.0).cpu().numpy()
+    dd, _ = orc.nn_kdtree(sc, mp)
+    assert np.array_equal(got, sc[dd < 30.0])
+    assert b200.remove_dynamic_points(torch.from_numpy(sc).cuda(), None).shape[0] == len(sc)
