@@ -273,6 +273,22 @@ def run_b200(args):
     executed = float(stats.evaluated_pairs.sum().item())
     assert torch.equal(stats.pose_total, out.pose_total)
     del stats
+    # untimed-for-the-headline A/B: the dense (no pruning) sweep of the same kernel, i.e. the
+    # brute-force FP32 roofline number; identical results required
+    os.environ["B200ICP_PRUNE"] = "0"
+    dense_out = m.alloc_outputs(P, N_POINTS, dev)
+    for _ in range(2):
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, out=dense_out)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(3):
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, out=dense_out)
+    d1.record()
+    torch.cuda.synchronize()
+    dense_ms = d0.elapsed_time(d1) / 3
+    os.environ.pop("B200ICP_PRUNE")
+    assert torch.equal(dense_out.pose_total, out.pose_total), "dense and pruned sweeps disagree"
+    del dense_out
 
     ms_per_step = total_ms / args.steps
     value = world * P / (ms_per_step * 1e-3)
@@ -329,6 +345,10 @@ def run_b200(args):
                                        "capture profiles/r1f_align_pruned_ncu_details.txt (algorithmic: 380.6 MB)",
                      "executed_pair_eval_fraction": executed / (P * PAIR_EVALS_PER_ALIGNMENT),
                      "executed_tflops": executed * FLOP_PER_PAIR_EVAL / (kernel_ms * 1e-3) / 1e12,
+                     "dense_sweep": {"kernel": "icp_align_warp_kernel<6,dense> (B200ICP_PRUNE=0: every pair-eval "
+                                               "executed; bit-identical poses)", "kernel_ms": dense_ms,
+                                     "achieved": flops / (dense_ms * 1e-3) / 1e12,
+                                     "frac": flops / (dense_ms * 1e-3) / 1e12 / fp32_peak},
                      "note": "achieved = brute-force-equivalent work (SURVEY.md 8d: N_src x N_tgt x iterations x 5 "
                              "FLOP) / time.  The sweep prunes target groups that are provably out of reach "
                              "(results identical to the full sweep, DESIGN.md 4.2), so fewer pair-evals are "

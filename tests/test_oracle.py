@@ -129,3 +129,26 @@ def test_live_reference_equals_oracle(cart_scans):
     Rr, tr = ref.best_fit_transform(P, Q)
     Ro, to = orc.best_fit_transform(P, Q)
     assert np.array_equal(Rr, Ro) and np.array_equal(tr, to)
+
+
+def test_c_oracle_matches_numpy_oracle(cart_scans):
+    """oracle/icp_oracle.c (brute force + closed form) walks the same index history as the
+    SciPy/SVD restatement on real scans, incl. gate and initial pose."""
+    from oracle import c_oracle
+    for p in (2, 350, 672, 1062):
+        A, B = cart_scans[p + 1], cart_scans[p]
+        o = orc.icp_extended(A, B, 30, 1e-5)
+        c = c_oracle.icp(A, B, 30, 1e-5, history=True)
+        assert c["iterations"] == o.iterations
+        assert all(np.array_equal(c["history"][i], o.indices[i]) for i in range(o.iterations))
+        assert np.allclose(c["pose_total"][:4].reshape(2, 2), o.R_tot, atol=1e-12)
+        assert np.allclose(c["pose_total"][4:], o.t_tot, atol=1e-8) and abs(c["error"] - o.error) < 1e-9
+    A, B = cart_scans[100], cart_scans[99]
+    init = [math.cos(0.01), -math.sin(0.01), math.sin(0.01), math.cos(0.01), 5.0, -3.0]
+    o = orc.icp_extended(A, B, 30, 1e-5, init_pose=(np.array(init[:4]).reshape(2, 2), np.array(init[4:])), max_corr_dist=120.0)
+    c = c_oracle.icp(A, B, 30, 1e-5, init_pose=init, max_corr_dist=120.0)
+    assert c["iterations"] == o.iterations and c["inliers"] == round(o.fitness * len(A))
+    assert np.allclose(c["pose_total"][4:], o.t_tot, atol=1e-8) and abs(c["rmse"] - o.rmse) < 1e-9
+    idx, d2 = c_oracle.nn_bruteforce(A, B)
+    d, i = orc.nn_kdtree(A, B)
+    assert np.array_equal(idx, i) and np.allclose(np.sqrt(d2), d, rtol=1e-15)
