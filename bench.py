@@ -451,7 +451,7 @@ def run_odometry(args):
         d_len = h_len.to(dev, non_blocking=True)
         tb = m.polar_to_cartesian(d_raw, d_len)
         res = m.align_consecutive(tb, max_iterations=30, tolerance=1e-5, out=out)
-        return m.chain_poses(res.pose_total)             # D2H of [1830,6] + host prefix composition
+        return m.chain_poses(res.pose_total)             # device prefix composition + D2H of [1831,6]
 
     e2e_ms = _timed(e2e_step, args.steps, args.warmup, barrier, max_over_ranks)
     lens = table.lengths.cpu().numpy().astype(np.int64)
@@ -475,7 +475,7 @@ def run_odometry(args):
         "e2e": {"value": n_pairs / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h_raw.numel() * 8 + h_len.numel() * 4),
                 "d2h_bytes_per_step": n_pairs * 48,
-                "api": "raw polar rows (host) -> polar_to_cartesian -> align_consecutive -> chain_poses (host)"},
+                "api": "raw polar rows (host) -> polar_to_cartesian -> align_consecutive -> chain_poses (device kernel) -> D2H of global poses"},
         "cpu_baseline": {"value": n_pairs / cpu_wall, "unit": "alignments/s", "cores": 1, "kind": "port",
                          "sample": f"all 1,830 pairs, oracle port of icp.py:5-53, {cpu_wall:.3f} s wall "
                                    f"(+ {cpu_prep:.3f} s for process.py:38-52's row loop); {its} iterations; {cpu_model()}",

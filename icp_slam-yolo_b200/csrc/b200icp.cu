@@ -1341,6 +1341,58 @@ __global__ void __launch_bounds__(256) select_scatter_kernel(const void* points,
 }
 
 // ------------------------------------------------------------------------------------
+// kernel: prefix composition of pairwise poses into global poses (sequence odometry:
+// T_{0,k+1} = T_{0,k} o T_k; the reference's SLAM loops carry the pose frame to frame,
+// duc/ICP_LIDAR/slam_offline.py:382-392).  One CTA, three phases: every thread composes a
+// contiguous segment, thread 0 scans the 1,024 segment totals, every thread rewrites its
+// segment with its prefix.  out[0] = identity, out[k+1] = out[k] o pose[k].
+// ------------------------------------------------------------------------------------
+struct Se2 {
+  double r00, r01, r10, r11, tx, ty;
+};
+__device__ __forceinline__ Se2 se2_identity() { return Se2{1.0, 0.0, 0.0, 1.0, 0.0, 0.0}; }
+__device__ __forceinline__ Se2 se2_load(const double* p) { return Se2{p[0], p[1], p[2], p[3], p[4], p[5]}; }
+__device__ __forceinline__ void se2_store(double* p, const Se2& a) {
+  p[0] = a.r00; p[1] = a.r01; p[2] = a.r10; p[3] = a.r11; p[4] = a.tx; p[5] = a.ty;
+}
+// a o b : first b, then a  (x -> Ra (Rb x + tb) + ta)
+__device__ __forceinline__ Se2 se2_mul(const Se2& a, const Se2& b) {
+  Se2 c;
+  c.r00 = a.r00 * b.r00 + a.r01 * b.r10; c.r01 = a.r00 * b.r01 + a.r01 * b.r11;
+  c.r10 = a.r10 * b.r00 + a.r11 * b.r10; c.r11 = a.r10 * b.r01 + a.r11 * b.r11;
+  c.tx = a.r00 * b.tx + a.r01 * b.ty + a.tx;
+  c.ty = a.r10 * b.tx + a.r11 * b.ty + a.ty;
+  return c;
+}
+
+__global__ void __launch_bounds__(1024) chain_poses_kernel(const double* __restrict__ poses, int64_t n,
+                                                           double* __restrict__ out) {
+  __shared__ double seg[1024][6];
+  const int tid = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t b = min(n, tid * per), e = min(n, b + per);
+  Se2 acc = se2_identity();
+  for (int64_t k = b; k < e; ++k) acc = se2_mul(acc, se2_load(poses + 6 * k));
+  se2_store(seg[tid], acc);
+  __syncthreads();
+  if (tid == 0) {                       // exclusive scan of the segment totals
+    Se2 run = se2_identity();
+    for (int q = 0; q < 1024; ++q) {
+      const Se2 t = se2_load(seg[q]);
+      se2_store(seg[q], run);
+      run = se2_mul(run, t);
+    }
+    se2_store(out, se2_identity());
+  }
+  __syncthreads();
+  acc = se2_load(seg[tid]);
+  for (int64_t k = b; k < e; ++k) {
+    acc = se2_mul(acc, se2_load(poses + 6 * k));
+    se2_store(out + 6 * (k + 1), acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // kernel: FP32 FFMA throughput probe (roofline denominator of the NN phase)
 // ------------------------------------------------------------------------------------
 constexpr int kProbeChains = 16;
@@ -1597,6 +1649,14 @@ int b200icp_select_points(const void* points, int32_t dtype, int64_t n, int32_t 
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "select_scatter_kernel");
   }
+  return B200ICP_OK;
+}
+
+int b200icp_chain_poses(const double* poses, int64_t n, double* out, void* stream) {
+  if (!poses || !out || n < 0) { set_error("chain_poses: bad arguments"); return B200ICP_ERR_INVALID_ARGUMENT; }
+  chain_poses_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(poses, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "chain_poses_kernel");
   return B200ICP_OK;
 }
 

@@ -22,8 +22,26 @@ def align_consecutive(table: ScanTable, *, max_iterations: int = 30, tolerance: 
                        tolerance=tolerance, max_corr_dist=max_corr_dist, out=out, **kw)
 
 
+def chain_poses_device(pose_total: torch.Tensor, stream=None) -> torch.Tensor:
+    """Prefix-compose pairwise poses [B,6] (CUDA, float64) into global poses [B+1,6] on the device."""
+    import ctypes as C
+    from . import _cabi
+    from .registration import _ptr, _require_cuda, _stream_ptr
+    if pose_total.dtype != torch.float64 or pose_total.dim() != 2 or pose_total.shape[1] != 6:
+        raise ValueError("pose_total must be float64 [B, 6]")
+    _require_cuda(pose_total, "pose_total")
+    out = torch.empty((pose_total.shape[0] + 1, 6), dtype=torch.float64, device=pose_total.device)
+    with torch.cuda.device(pose_total.device):
+        rc = _cabi.lib().b200icp_chain_poses(_ptr(pose_total), int(pose_total.shape[0]), _ptr(out), _stream_ptr(stream))
+    _cabi.check(rc, "b200icp_chain_poses")
+    return out
+
+
 def chain_poses(pose_total) -> np.ndarray:
-    """Prefix-compose pairwise poses [B,6] into global poses [B+1,6] (row 0 = identity)."""
+    """Prefix-compose pairwise poses [B,6] into global poses [B+1,6] (row 0 = identity).
+    CUDA tensors are composed on the device (one kernel); arrays on the host."""
+    if isinstance(pose_total, torch.Tensor) and pose_total.is_cuda:
+        return chain_poses_device(pose_total).cpu().numpy()
     p = pose_total.detach().cpu().numpy() if isinstance(pose_total, torch.Tensor) else np.asarray(pose_total)
     out = np.zeros((len(p) + 1, 6))
     R, t = np.eye(2), np.zeros(2)

@@ -215,6 +215,14 @@ int b200icp_select_points(const void* points, int32_t dtype, int64_t n, int32_t 
                           void* out_points, int64_t* count_out, int64_t* scratch, void* stream);
 
 /*
+ * Sequence odometry: prefix composition of the pairwise poses of consecutive scans into global
+ * poses, out[0] = identity, out[k+1] = out[k] o poses[k]  (the frame-to-frame pose carry of the
+ * reference's SLAM loops, duc/ICP_LIDAR/slam_offline.py:382-392).
+ *   poses [n][6], out [n+1][6], both R00 R01 R10 R11 tx ty, float64, device.
+ */
+int b200icp_chain_poses(const double* poses, int64_t n, double* out, void* stream);
+
+/*
  * FP32 FFMA throughput probe used as the roofline denominator of the NN phase
  * (MEASURED_PEAKS.json carries no FP32 figure).  Launches one kernel doing
  * `flop_out[0]` floating point operations (written to a HOST int64); the caller
