@@ -11,7 +11,7 @@ from .registration import (AlignResult, ScanTable, align_pairs, alloc_outputs,  
 from .odometry import align_consecutive, chain_poses         # noqa: F401
 from .sharding import shard_range, triangle_pair, triangle_pair_count   # noqa: F401
 from .scan_to_map import MapShard, ScanToMap, ScanToMapResult, scan_to_map_icp   # noqa: F401
-from .mapping import crop_local_map, remove_dynamic_points   # noqa: F401
+from .mapping import crop_local_map, remove_dynamic_points, voxel_down_sample   # noqa: F401
 from . import scan_io                                          # noqa: F401
 
 __all__ = [
@@ -19,5 +19,5 @@ __all__ = [
     "registration_p2p", "AlignResult", "ScanTable", "align_pairs", "alloc_outputs", "ffma_probe",
     "nn_search", "polar_to_cartesian", "align_consecutive", "chain_poses", "shard_range",
     "triangle_pair", "triangle_pair_count", "scan_io", "MapShard", "ScanToMap", "ScanToMapResult",
-    "scan_to_map_icp", "crop_local_map", "remove_dynamic_points",
+    "scan_to_map_icp", "crop_local_map", "remove_dynamic_points", "voxel_down_sample",
 ]

@@ -72,6 +72,9 @@ SYMBOLS = {
     "b200icp_select_points": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_double,
                                         C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200icp_chain_poses": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200icp_voxel_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "b200icp_voxel_downsample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_void_p]),
     "b200icp_s2m_chunk": (C.c_int, []),
     "b200icp_s2m_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p]),

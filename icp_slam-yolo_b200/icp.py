@@ -103,10 +103,11 @@ def nearest_neighbors(src, tgt) -> Tuple[np.ndarray, np.ndarray]:
     return np.sqrt(d2[0].cpu().numpy()), idx[0].cpu().numpy().astype(np.intp)
 
 
-def registration_p2p(points1, points2, threshold: float = 200.0, trans_init=None,
-                     max_iteration: int = 50, tolerance: float = 1e-5):
+def registration_p2p(points1, points2, threshold: float = 200.0, voxel_size: Optional[float] = None,
+                     trans_init=None, max_iteration: int = 50, tolerance: float = 1e-5):
     """Open3D-shaped point-to-point adapter: ``(rmse, T4x4)``.
 
+    Positional-compatible with ``gicp(points1, points2, threshold, voxel_size, trans_init)``.
     Mirrors the call shape of ``gicp(points1, points2, threshold, voxel, trans_init)``
     (duc/ICP_LIDAR/gicp_lidar.py:12-36; caller duc/ICP_LIDAR/mainn.py:311) and of
     ``icp(...)`` in duc/code python/b.py:219-236, including the ``< 10`` points guard
@@ -117,6 +118,10 @@ def registration_p2p(points1, points2, threshold: float = 200.0, trans_init=None
     p2 = np.asarray(points2, dtype=np.float64)
     if len(p1) < 10 or len(p2) < 10:
         return float("inf"), np.eye(4)
+    if voxel_size:                       # gicp_lidar.py:20-21: both clouds are down-sampled first
+        from .mapping import voxel_down_sample
+        p1 = voxel_down_sample(torch.from_numpy(np.ascontiguousarray(p1[:, :2])).cuda(), voxel_size).cpu().numpy()
+        p2 = voxel_down_sample(torch.from_numpy(np.ascontiguousarray(p2[:, :2])).cuda(), voxel_size).cpu().numpy()
     o = icp_full(p1, p2, max_iteration, tolerance,
                  init_pose=None if trans_init is None else np.asarray(trans_init),
                  max_corr_dist=threshold)

@@ -59,3 +59,26 @@ def remove_dynamic_points(current_points: torch.Tensor, prev_points: Optional[to
         s2m.search()
         key = s2m.records[:, 0].contiguous()
     return _select(current_points, 0, key, 0.0, 0.0, float(distance_threshold) ** 2)
+
+
+def voxel_down_sample(points: torch.Tensor, voxel_size: float, stream=None) -> torch.Tensor:
+    """One point per occupied 2D cell ``floor(p / voxel_size)`` (the mean of its points), cells
+    ordered by (cell_y, cell_x): ``point_cloud.voxel_down_sample(voxel_size)`` as the reference
+    applies it before registration (gicp_lidar.py:8-11,20-21) and in remove_duplicate_points
+    (process.py:68-73)."""
+    if points.dim() != 2 or points.shape[1] != 2 or points.dtype not in _DTYPES:
+        raise ValueError("points must be [n, 2] float32/float64")
+    _require_cuda(points, "points")
+    n = int(points.shape[0])
+    if n == 0:
+        return points
+    lib = _cabi.lib()
+    wb = lib.b200icp_voxel_workspace_bytes(n)
+    ws = torch.empty(wb, dtype=torch.uint8, device=points.device)
+    out = torch.empty_like(points)
+    count = torch.zeros(1, dtype=torch.int64, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = lib.b200icp_voxel_downsample(_ptr(points), _DTYPES[points.dtype], n, float(voxel_size), _ptr(out),
+                                          _ptr(count), _ptr(ws), wb, _stream_ptr(stream))
+    _cabi.check(rc, "b200icp_voxel_downsample")
+    return out[: int(count.item())]

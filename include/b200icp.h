@@ -223,6 +223,19 @@ int b200icp_select_points(const void* points, int32_t dtype, int64_t n, int32_t 
 int b200icp_chain_poses(const double* poses, int64_t n, double* out, void* stream);
 
 /*
+ * 2D voxel-grid down-sampling: one point per occupied cell (cell = floor(p / voxel_size)), the
+ * mean of the points in it, cells ordered by (cell_y, cell_x).  Replaces
+ * point_cloud.voxel_down_sample(voxel_size) as the reference uses it before registration
+ * (duc/ICP_LIDAR/gicp_lidar.py:8-11,20-21) and for duplicate removal (process.py:68-73); the 2D
+ * grid is labels_segmentation/d.py:10-16.  Parity-unpinned against Open3D (output order of
+ * Open3D is unspecified).  out_points [n][2] (same dtype), count_out device int64.
+ */
+int64_t b200icp_voxel_workspace_bytes(int64_t n);
+int b200icp_voxel_downsample(const void* points, int32_t dtype, int64_t n, double voxel_size,
+                             void* out_points, int64_t* count_out, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
+/*
  * FP32 FFMA throughput probe used as the roofline denominator of the NN phase
  * (MEASURED_PEAKS.json carries no FP32 figure).  Launches one kernel doing
  * `flop_out[0]` floating point operations (written to a HOST int64); the caller

@@ -362,3 +362,30 @@ def synth_trajectory_scans(n_scans, n_points=360, seed=4096, dtype=np.float32):
     wy = r * np.sin(phi) - pos[:, 1:2]
     c, s = np.cos(th)[:, None], np.sin(th)[:, None]
     return np.stack([wx * c + wy * s, wy * c - wx * s], axis=2).astype(dtype)
+
+
+# ----------------------------------------------------------------------------
+# voxel-grid down-sampling as the reference applies it before registration
+# (gicp_lidar.py:8-11,20-21 -> Open3D voxel_down_sample; 2D grid as in d.py:10-16)
+# ----------------------------------------------------------------------------
+def voxel_down_sample_2d(points, voxel_size):
+    """One point per occupied cell floor(p / voxel_size): the mean of its points, cells ordered by
+    (cell_y, cell_x).  PARITY-UNPINNED against Open3D (not vendored; its output order is the
+    iteration order of a hash map); this function is the definition the CUDA path is held to."""
+    p = np.asarray(points, dtype=np.float64)[:, :2]
+    if len(p) == 0:
+        return p.copy()
+    inv = 1.0 / float(voxel_size)
+    gx = np.floor(p[:, 0] * inv).astype(np.int64)
+    gy = np.floor(p[:, 1] * inv).astype(np.int64)
+    order = np.lexsort((np.arange(len(p)), gx, gy))            # stable: (gy, gx), then input order
+    gxs, gys = gx[order], gy[order]
+    head = np.ones(len(p), dtype=bool)
+    head[1:] = (gxs[1:] != gxs[:-1]) | (gys[1:] != gys[:-1])
+    seg = np.cumsum(head) - 1
+    out = np.zeros((seg[-1] + 1, 2))
+    cnt = np.zeros(seg[-1] + 1)
+    for q in range(len(p)):                                    # sequential sums, input order per cell
+        out[seg[q]] += p[order[q]]
+        cnt[seg[q]] += 1.0
+    return out * (1.0 / cnt)[:, None]

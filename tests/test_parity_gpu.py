@@ -401,3 +401,21 @@ def test_local_map_crop_and_dynamic_point_removal(b200, cart_scans):
     dd, _ = orc.nn_kdtree(sc, mp)
     assert np.array_equal(got, sc[dd < 30.0])
     assert b200.remove_dynamic_points(torch.from_numpy(sc).cuda(), None).shape[0] == len(sc)
+
+
+def test_voxel_down_sample_and_gicp_shaped_call(b200, cart_scans):
+    """gicp_lidar.py:8-11,20-21 (voxel_down_sample before registration), d.py:10-16 (2D grid)."""
+    rng = np.random.default_rng(2)
+    for pts, vox in ((cart_scans[800], 50.0), (rng.uniform(-3000, 3000, (20000, 2)), 70.0),
+                     (np.array([[0.1, 0.1], [0.2, 0.3], [-0.1, 0.1], [5.0, 5.0]]), 1.0)):
+        ref = orc.voxel_down_sample_2d(pts, vox)
+        for dt, tol in ((np.float64, 1e-9), (np.float32, 1e-3)):
+            got = b200.voxel_down_sample(torch.from_numpy(pts.astype(dt)).cuda(), vox).cpu().numpy()
+            ref_dt = orc.voxel_down_sample_2d(pts.astype(dt), vox)
+            assert got.shape == ref_dt.shape and np.allclose(got, ref_dt, rtol=0, atol=tol)
+        assert len(ref) <= len(pts)
+    A, B = cart_scans[801], cart_scans[800]
+    rmse, T = b200.registration_p2p(np.c_[A, np.zeros(len(A))], np.c_[B, np.zeros(len(B))], 200.0, 20.0, np.eye(4))
+    a, b_ = orc.voxel_down_sample_2d(A, 20.0), orc.voxel_down_sample_2d(B, 20.0)
+    o = orc.icp_extended(a, b_, 50, 1e-5, init_pose=(np.eye(2), np.zeros(2)), max_corr_dist=200.0)
+    assert abs(rmse - o.rmse) < 1e-7 and np.allclose(T[:2, :2], o.R_tot, atol=1e-9) and np.allclose(T[:2, 3], o.t_tot, atol=1e-5)
