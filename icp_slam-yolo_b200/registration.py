@@ -298,6 +298,12 @@ class HostPipeline:
         self.n_pairs, self.src_pitch, self.tgt_pitch = int(n_pairs), int(src_pitch), int(tgt_pitch)
         self.device = torch.device(device)
         self.chunk = max(1, -(-self.n_pairs // max(1, chunks)))
+        # chunk boundaries: a short first chunk (1/4 of a regular one) so that the exposed part of
+        # the pipeline -- the first host-to-device copy -- is small; the rest are regular
+        first = max(1, self.chunk // 4)
+        self.bounds = [0, min(first, self.n_pairs)]
+        while self.bounds[-1] < self.n_pairs:
+            self.bounds.append(min(self.n_pairs, self.bounds[-1] + self.chunk))
         self.dtype = dtype
         c = self.chunk
         mk = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, device=self.device)
@@ -327,10 +333,8 @@ class HostPipeline:
         ready = [None, None]       # compute-done events per staging buffer
         drained = [None, None]     # results-copied events per staging buffer
         self.launches = 0
-        n_chunks = -(-self.n_pairs // self.chunk)
-        for ci in range(n_chunks):
-            b0 = ci * self.chunk
-            b1 = min(self.n_pairs, b0 + self.chunk)
+        for ci in range(len(self.bounds) - 1):
+            b0, b1 = self.bounds[ci], self.bounds[ci + 1]
             nb = b1 - b0
             buf = self.bufs[ci & 1]
             with torch.cuda.stream(self.copy_stream):
