@@ -419,3 +419,22 @@ def test_voxel_down_sample_and_gicp_shaped_call(b200, cart_scans):
     a, b_ = orc.voxel_down_sample_2d(A, 20.0), orc.voxel_down_sample_2d(B, 20.0)
     o = orc.icp_extended(a, b_, 50, 1e-5, init_pose=(np.eye(2), np.zeros(2)), max_corr_dist=200.0)
     assert abs(rmse - o.rmse) < 1e-7 and np.allclose(T[:2, :2], o.R_tot, atol=1e-9) and np.allclose(T[:2, 3], o.t_tot, atol=1e-5)
+
+
+def test_host_pipeline_matches_resident_path(b200, cart_scans):
+    """HostPipeline (pinned host tables, chunked H2D || kernel || D2H) == align_pairs on resident
+    tensors, ragged rows included, chunk boundaries not multiples of anything."""
+    A = [cart_scans[p + 1] for p in range(300, 437)]
+    B = [cart_scans[p] for p in range(300, 437)]
+    hs, hsl = b200.ScanTable.pack_host(A, dtype=np.float64, pin=True)
+    ht, htl = b200.ScanTable.pack_host(B, dtype=np.float64, pin=True)
+    pipe = b200.registration.HostPipeline(len(A), hs.shape[1], ht.shape[1], dtype=torch.float64, chunks=5)
+    pose, err, its = pipe.run(hs, ht, hsl, htl, max_iterations=30, tolerance=1e-5)
+    torch.cuda.synchronize()
+    ref = b200.align_pairs(b200.ScanTable(hs.cuda(), hsl.cuda()), b200.ScanTable(ht.cuda(), htl.cuda()),
+                           max_iterations=30, tolerance=1e-5)
+    assert torch.equal(pose, ref.pose_total.cpu()) and torch.equal(err, ref.error.cpu())
+    assert torch.equal(its, ref.iterations.cpu()) and pipe.launches == len(pipe.bounds) - 1
+    pose2, _, _ = pipe.run(hs, ht, hsl, htl, max_iterations=30, tolerance=1e-5)      # buffers are reusable
+    torch.cuda.synchronize()
+    assert torch.equal(pose2, ref.pose_total.cpu())
