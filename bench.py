@@ -543,7 +543,8 @@ def run_scan2map(args):
     shard = m.MapShard(torch.from_numpy(full[b:e]).to(dev), global_offset=b)
     del full
     scan = torch.from_numpy(orc.synth_scan_for_map(N)).to(dev)
-    s2m = m.ScanToMap(shard, N)
+    exchange = os.environ.get("B200ICP_S2M_EXCHANGE", "nccl")
+    s2m = m.ScanToMap(shard, N, exchange=exchange)
     fp32_peak = m.ffma_probe()
 
     def step():
@@ -576,7 +577,8 @@ def run_scan2map(args):
         "config": {"workload": "configs[4]: scan-to-map ICP, %d-point scan vs %d-point map, 30 forced iterations" % (N, M),
                    "map_points_this_rank": e - b,
                    "l2": "map shard SoA (%.0f MB) streams from L2/HBM every iteration" % ((e - b) * 8 / 1e6),
-                   "parallelism": "map sharded contiguously; all_gather of 32 B records per iteration (%d B per rank)" % (N * 32),
+                   "parallelism": "map sharded contiguously; %s all-gather of 32 B records per iteration (%d B per rank)" % (
+                       "peer-store (NVLink, b200icp_s2m_publish/wait)" if exchange == "peer" else "NCCL", N * 32),
                    "final_error_mm": res.error},
         "gpu_launches": args.steps * s2m.launches,
         "roofline": {"bound": "fp32", "kernel": "s2m_sweep_kernel (+ resolve/exact)",

@@ -82,6 +82,13 @@ SYMBOLS = {
                                    C.c_void_p, C.c_void_p]),
     "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200icp_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "b200icp_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200icp_peer_close": (C.c_int, [C.c_void_p]),
+    "b200icp_peer_free": (C.c_int, [C.c_void_p]),
+    "b200icp_s2m_publish": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200icp_s2m_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "b200icp_s2m_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

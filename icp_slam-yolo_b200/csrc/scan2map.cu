@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 
 #include "b200icp.h"
 
@@ -626,6 +627,63 @@ __global__ void __launch_bounds__(1024) s2m_update_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// peer exchange: the all-gather of the records fused into a store-to-every-peer kernel.
+// Every rank owns one peer-visible buffer  [2 slots][world][n] records + [2][world] int64 flags.
+// publish: each thread stores its 32-byte record into slot `slot`, row `rank` of EVERY rank's
+// buffer (NVLink peer stores), then the last CTA raises flags[slot][rank] = seq on every rank
+// (system-scope release).  wait: spins (system-scope acquire) until all `world` flags of the
+// slot reached seq.  Slots alternate per iteration, which is enough: a peer can publish
+// iteration k+2 only after it has seen this rank's k+1, i.e. after this rank finished reading k.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) s2m_publish_kernel(const b200icp_s2m_record* __restrict__ local,
+                                                          int n, void* const* __restrict__ peers, int world,
+                                                          int rank, int slot, long long seq,
+                                                          unsigned int* __restrict__ block_counter,
+                                                          const b200icp_s2m_state* __restrict__ state) {
+  if (state->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double4 v = reinterpret_cast<const double4*>(local)[i];
+    for (int r = 0; r < world; ++r) {
+      double4* dst = reinterpret_cast<double4*>(peers[r]) + ((int64_t)slot * world + rank) * n + i;
+      *dst = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(block_counter, 1u);
+    if (done == gridDim.x - 1) {                       // last CTA: every record of this rank is out
+      *block_counter = 0;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) {
+        long long* flags = reinterpret_cast<long long*>(reinterpret_cast<double4*>(peers[r]) + (int64_t)2 * world * n);
+        asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(flags + slot * world + rank), "l"(seq) : "memory");
+      }
+    }
+  }
+}
+
+__global__ void s2m_wait_kernel(const void* mine, int n, int world, int slot, long long seq,
+                                b200icp_s2m_state* state) {
+  if (state->done) return;
+  const long long* flags = reinterpret_cast<const long long*>(reinterpret_cast<const double4*>(mine) + (int64_t)2 * world * n);
+  if ((int)threadIdx.x < world) {
+    const long long* f = flags + slot * world + threadIdx.x;
+    const long long t0 = clock64();
+    long long v = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > 4000000000LL) {            // ~2 s: a peer is gone; fail instead of hanging
+        state->done = 2;
+        break;
+      }
+    }
+  }
+}
+
 int fail(const char* msg, int code) {
   b200icp_set_error_str(msg);
   return code;
@@ -742,6 +800,58 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int3
   s2m_exact_reduce_kernel<<<32, 256, 0, st>>>(shard->points, shard->dtype, shard->global_offset,
                                               amb_list, amb_count, exact_partials, records, state);
   return cuda_check("s2m_exact_reduce_kernel");
+}
+
+int b200icp_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out) {
+  if (bytes < 1 || !ptr_out || !handle_out) return fail("peer_alloc: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return cuda_check("cudaMalloc");
+  if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess) return cuda_check("cudaMemset");
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return cuda_check("cudaIpcGetMemHandle"); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &h, 64);
+  *ptr_out = p;
+  return B200ICP_OK;
+}
+
+int b200icp_peer_open(const void* handle, void** ptr_out) {
+  if (!handle || !ptr_out) return fail("peer_open: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return cuda_check("cudaIpcOpenMemHandle");
+  *ptr_out = p;
+  return B200ICP_OK;
+}
+
+int b200icp_peer_close(void* ptr) {
+  if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) return cuda_check("cudaIpcCloseMemHandle");
+  return B200ICP_OK;
+}
+
+int b200icp_peer_free(void* ptr) {
+  if (ptr && cudaFree(ptr) != cudaSuccess) return cuda_check("cudaFree");
+  return B200ICP_OK;
+}
+
+int b200icp_s2m_publish(const b200icp_s2m_record* records, int32_t n, void* const* peers, int32_t world,
+                        int32_t rank, int32_t slot, int64_t seq, void* counter,
+                        const b200icp_s2m_state* state, void* stream) {
+  if (!records || !peers || !counter || !state || n < 1 || world < 1 || rank < 0 || rank >= world || (slot != 0 && slot != 1))
+    return fail("s2m_publish: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
+  s2m_publish_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      records, n, peers, world, rank, slot, (long long)seq, reinterpret_cast<unsigned int*>(counter), state);
+  return cuda_check("s2m_publish_kernel");
+}
+
+int b200icp_s2m_wait(const void* my_buffer, int32_t n, int32_t world, int32_t slot, int64_t seq,
+                     b200icp_s2m_state* state, void* stream) {
+  if (!my_buffer || !state || n < 1 || world < 1 || world > 1024 || (slot != 0 && slot != 1))
+    return fail("s2m_wait: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
+  s2m_wait_kernel<<<1, ((world + 31) / 32) * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      my_buffer, n, world, slot, (long long)seq, state);
+  return cuda_check("s2m_wait_kernel");
 }
 
 int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, double* src64,

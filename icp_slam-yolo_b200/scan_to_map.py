@@ -74,14 +74,74 @@ class ScanToMapResult:
     src: torch.Tensor                    # [n,2] float64 transformed scan (device)
 
 
-class ScanToMap:
-    """Reusable buffers for registering n-point scans against one shard (per rank)."""
+class PeerExchange:
+    """Peer-visible record buffers of all ranks (CUDA IPC), for the store-to-every-peer all-gather
+    (b200icp_s2m_publish / b200icp_s2m_wait).  Layout per rank: [2 slots][world][n] records, then
+    [2][world] int64 flags.  NCCL is used once, to exchange the 64-byte IPC handles."""
 
-    def __init__(self, shard: MapShard, n_scan: int, group=None, want_indices: bool = False):
+    def __init__(self, n: int, world: int, rank: int, group, device):
+        import torch.distributed as dist
+        self.n, self.world, self.rank, self.device = n, world, rank, device
+        self.slot_bytes = world * n * RECORD_BYTES
+        nbytes = 2 * self.slot_bytes + 2 * world * 8
+        lib = _lib()
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _cabi.check(lib.b200icp_peer_alloc(nbytes, C.byref(ptr), handle), "b200icp_peer_alloc")
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
+            everyone = torch.empty(world * 64, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+            handles = everyone.cpu().numpy().reshape(world, 64)
+            self.base = int(ptr.value)
+            self.opened = []
+            addrs = []
+            for r in range(world):
+                if r == rank:
+                    addrs.append(self.base)
+                    continue
+                p = C.c_void_p()
+                _cabi.check(lib.b200icp_peer_open(handles[r].tobytes(), C.byref(p)), "b200icp_peer_open")
+                self.opened.append(int(p.value))
+                addrs.append(int(p.value))
+            self.peers = torch.tensor(addrs, dtype=torch.int64, device=device)
+            self.counter = torch.zeros(4, dtype=torch.int32, device=device)
+            self.seq = 0
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+
+    def slot_ptr(self, slot: int) -> C.c_void_p:
+        return C.c_void_p(self.base + slot * self.slot_bytes)
+
+    def close(self):
+        import torch.distributed as dist
+        lib = _lib()
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        for p in self.opened:
+            lib.b200icp_peer_close(C.c_void_p(p))
+        self.opened = []
+        if self.base:
+            lib.b200icp_peer_free(C.c_void_p(self.base))
+            self.base = 0
+
+
+class ScanToMap:
+    """Reusable buffers for registering n-point scans against one shard (per rank).
+
+    exchange = "nccl": records all-gathered with torch.distributed (default);
+    exchange = "peer": every rank stores its records straight into every peer's buffer over
+    NVLink and raises a flag there (PeerExchange) -- no library collective in the loop."""
+
+    def __init__(self, shard: MapShard, n_scan: int, group=None, want_indices: bool = False,
+                 exchange: str = "nccl"):
         import torch.distributed as dist
         self.shard, self.n = shard, int(n_scan)
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.exchange = exchange if self.world > 1 else "nccl"
+        self.peer = None
         dev = shard.points.device
         self.dev = dev
         self.src64 = torch.empty((self.n, 2), dtype=torch.float64, device=dev)
@@ -95,6 +155,10 @@ class ScanToMap:
         self.workspace = torch.empty(wb, dtype=torch.uint8, device=dev)
         self.indices = torch.empty(self.n, dtype=torch.int32, device=dev) if want_indices else None
         self.launches = 0
+        if self.exchange == "peer":
+            self.peer = PeerExchange(self.n, self.world, self.rank, group, dev)
+        elif self.exchange != "nccl":
+            raise ValueError("exchange must be 'nccl' or 'peer'")
 
     def search(self, stream=None):
         """records <- exact nearest point of this shard for the current scan state."""
@@ -122,13 +186,26 @@ class ScanToMap:
             self.launches += 1
             for _ in range(int(max_iterations)):
                 self.search()
-                if self.world > 1:
+                if self.world > 1 and self.peer is not None:
+                    pe = self.peer
+                    pe.seq += 1
+                    slot = pe.seq & 1
+                    rc = _lib().b200icp_s2m_publish(_ptr(self.records), self.n, _ptr(pe.peers), self.world,
+                                                    self.rank, slot, pe.seq, _ptr(pe.counter),
+                                                    _ptr(self.state), _stream_ptr(None))
+                    _cabi.check(rc, "b200icp_s2m_publish")
+                    rc = _lib().b200icp_s2m_wait(C.c_void_p(pe.base), self.n, self.world, slot, pe.seq,
+                                                 _ptr(self.state), _stream_ptr(None))
+                    _cabi.check(rc, "b200icp_s2m_wait")
+                    self.launches += 2
+                    rec_all, ranks = pe.slot_ptr(slot), self.world
+                elif self.world > 1:
                     dist.all_gather_into_tensor(self.records_all.view(self.world * self.n, 4),
                                                 self.records, group=self.group)
-                    rec_all, ranks = self.records_all, self.world
+                    rec_all, ranks = _ptr(self.records_all), self.world
                 else:
-                    rec_all, ranks = self.records, 1
-                rc = _lib().b200icp_s2m_update(_ptr(rec_all), ranks, _ptr(self.src64), self.n,
+                    rec_all, ranks = _ptr(self.records), 1
+                rc = _lib().b200icp_s2m_update(rec_all, ranks, _ptr(self.src64), self.n,
                                                int(max_iterations), float(tolerance),
                                                0.0 if max_corr_dist is None else float(max_corr_dist),
                                                _ptr(self.indices), _ptr(self.state), _stream_ptr(None))

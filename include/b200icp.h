@@ -202,6 +202,29 @@ int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, d
                        int32_t* idx_out /*[n]|NULL*/, b200icp_s2m_state* state, void* stream);
 
 /*
+ * Peer exchange for scan-to-map: the all-gather of the records done by the GPUs themselves over
+ * NVLink peer stores instead of a library collective.  Every rank allocates one peer-visible
+ * buffer (b200icp_peer_alloc: cudaMalloc + IPC handle; layout [2 slots][world][n] records followed
+ * by [2][world] int64 flags), exchanges the 64-byte handles out of band, opens the others
+ * (b200icp_peer_open) and passes the DEVICE array of the `world` buffer addresses (own buffer at
+ * [rank]) to b200icp_s2m_publish, which stores this rank's records into every rank's buffer and
+ * then raises this rank's flag there.  b200icp_s2m_wait blocks the stream until all flags of the
+ * slot reached `seq` (2 s timeout -> state.done = 2).  Slots alternate per iteration; `seq` must
+ * grow monotonically over the life of the buffer.  b200icp_s2m_update then reads
+ * buffer + slot * world * n records.
+ */
+int b200icp_peer_alloc(int64_t bytes, void** ptr_out /*host*/, void* handle_out /*host, 64 bytes*/);
+int b200icp_peer_open(const void* handle /*host, 64 bytes*/, void** ptr_out /*host*/);
+int b200icp_peer_close(void* ptr);
+int b200icp_peer_free(void* ptr);
+int b200icp_s2m_publish(const b200icp_s2m_record* records, int32_t n, void* const* peers /*device*/,
+                        int32_t world, int32_t rank, int32_t slot, int64_t seq,
+                        void* counter /*device uint32, zeroed*/, const b200icp_s2m_state* state,
+                        void* stream);
+int b200icp_s2m_wait(const void* my_buffer, int32_t n, int32_t world, int32_t slot, int64_t seq,
+                     b200icp_s2m_state* state, void* stream);
+
+/*
  * Order-preserving selection of points (the steps either side of registration in the SLAM loop).
  *   mode 0: keep point i iff key[i] < threshold.  With key = squared NN distance to the previous
  *           scan (b200icp_nn_batch / b200icp_s2m_search) and threshold = d^2 this replaces

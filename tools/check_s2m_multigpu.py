@@ -26,8 +26,10 @@ def main():
     scan_np = orc.synth_scan_for_map(N)
     b, e = m.shard_range(M, rank, world)
     shard = m.MapShard(torch.from_numpy(full[b:e]).to(dev), global_offset=b)
-    s2m = m.ScanToMap(shard, N, want_indices=True)
+    exchange = os.environ.get("B200ICP_S2M_EXCHANGE", "nccl")
+    s2m = m.ScanToMap(shard, N, want_indices=True, exchange=exchange)
     res = s2m.run(torch.from_numpy(scan_np).to(dev), max_iterations=iters, tolerance=-1.0)
+    res = s2m.run(torch.from_numpy(scan_np).to(dev), max_iterations=iters, tolerance=-1.0)   # buffers reusable
     state = s2m.state.clone()
     gathered = [torch.empty_like(state) for _ in range(world)]
     dist.all_gather(gathered, state)
@@ -37,9 +39,11 @@ def main():
         ok_idx = np.array_equal(res.indices.cpu().numpy(), o.indices[-1])
         dR = float(np.max(np.abs(res.R - o.R_tot)))
         dt = float(np.max(np.abs(res.t - o.t_tot)))
-        print(f"world={world} state bit-identical across ranks: {same}; last-iteration indices == oracle: {ok_idx}; "
+        print(f"exchange={exchange} world={world} state bit-identical across ranks: {same}; last-iteration indices == oracle: {ok_idx}; "
               f"|dR|={dR:.2e} |dt|={dt:.2e} mm; error={res.error:.9f} (oracle {o.error:.9f})", flush=True)
         assert same and ok_idx and dR < 1e-9 and dt < 1e-6
+    if s2m.peer is not None:
+        s2m.peer.close()
     dist.barrier()
     dist.destroy_process_group()
 
