@@ -80,7 +80,9 @@ SYMBOLS = {
     "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p]),
     "b200icp_s2m_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
-    "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p,
+    "b200icp_s2m_bound": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b200icp_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "b200icp_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -387,6 +387,12 @@ __global__ void __launch_bounds__(128) s2m_resolve_kernel(
   float g_ub = CUDART_INF_F, g_lb1 = CUDART_INF_F, g_lb2 = CUDART_INF_F;
   uint32_t where = 0;
   const int n_items = (tile_count[i / kSrcPerCta] + kSegChunks - 1) / kSegChunks;
+  if (n_items == 0) {            // every chunk of this shard is out of reach: another rank holds the NN
+    b200icp_s2m_record none;
+    none.d2 = CUDART_INF; none.gidx = 0x7fffffffffffffffLL; none.bx = 0.0; none.by = 0.0;
+    records[i] = none;
+    return;
+  }
   for (int s = 0; s < n_items; ++s) {
     const Partial p = partials[(int64_t)s * n + i];
     merge_partial(g_ub, g_lb1, g_lb2, where, p.ub, p.lb1, p.lb2, p.where);
@@ -699,7 +705,7 @@ int cuda_check(const char* what) {
 }
 
 struct Workspace {        // byte offsets inside the caller's workspace
-  int64_t amb_list, ub, tile_count, tile_list, partials, exact, total;
+  int64_t amb_list, tile_count, tile_list, partials, exact, total;
   int n_items, tiles;
 };
 
@@ -711,7 +717,6 @@ Workspace layout_workspace(int n, int64_t m) {
   w.n_items = (int)((n_chunks + kSegChunks - 1) / kSegChunks);
   int64_t off = 256;                                         // [0]: ambiguous-source counter
   w.amb_list = off;   off += up((int64_t)n * 4);
-  w.ub = off;         off += up((int64_t)n * 4);
   w.tile_count = off; off += up((int64_t)w.tiles * 4);
   w.tile_list = off;  off += up((int64_t)w.tiles * n_chunks * 4);
   w.partials = off;   off += up((int64_t)w.n_items * n * (int64_t)sizeof(Partial));
@@ -754,10 +759,21 @@ int b200icp_s2m_init(const void* scan, int32_t dtype, int32_t n, const double* i
   return cuda_check("s2m_init_kernel");
 }
 
-int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int32_t n,
+int b200icp_s2m_bound(const b200icp_s2m_shard* shard, const double* src64, int32_t n, float* ub,
+                      const b200icp_s2m_state* state, void* stream) {
+  if (!shard || !src64 || !ub || !state || n < 1) return fail("s2m_bound: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n_chunks = (int)((shard->m + kChunk - 1) / kChunk);
+  if (cudaMemsetAsync(ub, 0x7f, (size_t)n * 4, st) != cudaSuccess) return cuda_check("cudaMemsetAsync");
+  s2m_bound_kernel<<<dim3((n + 127) / 128, (n_chunks + kBoundChunks - 1) / kBoundChunks), 128, 0, st>>>(
+      shard->chunk_origin, shard->chunk_radius, n_chunks, src64, n, ub, state);
+  return cuda_check("s2m_bound_kernel");
+}
+
+int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int32_t n, const float* ub,
                        b200icp_s2m_record* records, void* workspace, int64_t workspace_bytes,
                        const b200icp_s2m_state* state, void* stream) {
-  if (!shard || !src64 || !records || !workspace || !state || n < 1)
+  if (!shard || !src64 || !ub || !records || !workspace || !state || n < 1)
     return fail("s2m_search: bad arguments", B200ICP_ERR_INVALID_ARGUMENT);
   if (workspace_bytes < b200icp_s2m_workspace_bytes(n, shard->m))
     return fail("s2m_search: workspace too small", B200ICP_ERR_INVALID_ARGUMENT);
@@ -767,16 +783,11 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int3
   unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
   int32_t* amb_count = reinterpret_cast<int32_t*>(base);
   int32_t* amb_list = reinterpret_cast<int32_t*>(base + w.amb_list);
-  float* ub = reinterpret_cast<float*>(base + w.ub);
   int32_t* tile_count = reinterpret_cast<int32_t*>(base + w.tile_count);
   int32_t* tile_list = reinterpret_cast<int32_t*>(base + w.tile_list);
   Partial* partials = reinterpret_cast<Partial*>(base + w.partials);
   if (cudaMemsetAsync(amb_count, 0, 64, st) != cudaSuccess) return cuda_check("cudaMemsetAsync");
-  if (cudaMemsetAsync(ub, 0x7f, (size_t)n * 4, st) != cudaSuccess) return cuda_check("cudaMemsetAsync");
-  s2m_bound_kernel<<<dim3((n + 127) / 128, (n_chunks + kBoundChunks - 1) / kBoundChunks), 128, 0, st>>>(
-      shard->chunk_origin, shard->chunk_radius, n_chunks, src64, n, ub, state);
-  int rc = cuda_check("s2m_bound_kernel");
-  if (rc) return rc;
+  int rc = B200ICP_OK;
   s2m_cull_kernel<<<w.tiles, 256, 0, st>>>(shard->chunk_origin, shard->chunk_radius, n_chunks, src64, n,
                                           ub, tile_count, tile_list, state);
   rc = cuda_check("s2m_cull_kernel");

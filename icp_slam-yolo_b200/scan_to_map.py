@@ -134,11 +134,12 @@ class ScanToMap:
     NVLink and raises a flag there (PeerExchange) -- no library collective in the loop."""
 
     def __init__(self, shard: MapShard, n_scan: int, group=None, want_indices: bool = False,
-                 exchange: str = "nccl"):
+                 exchange: str = "nccl", local_only: bool = False):
         import torch.distributed as dist
         self.shard, self.n = shard, int(n_scan)
         self.group = group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = (dist.get_world_size(group)
+                      if (not local_only and dist.is_available() and dist.is_initialized()) else 1)
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.exchange = exchange if self.world > 1 else "nccl"
         self.peer = None
@@ -147,6 +148,7 @@ class ScanToMap:
         self.src64 = torch.empty((self.n, 2), dtype=torch.float64, device=dev)
         self.state = torch.zeros(STATE_BYTES // 8, dtype=torch.float64, device=dev)
         self.records = torch.empty((self.n, 4), dtype=torch.float64, device=dev)          # 32 B each
+        self.ub = torch.empty(self.n, dtype=torch.float32, device=dev)
         self.records_all = (torch.empty((self.world, self.n, 4), dtype=torch.float64, device=dev)
                             if self.world > 1 else None)
         wb = _lib().b200icp_s2m_workspace_bytes(self.n, shard.m)
@@ -161,8 +163,15 @@ class ScanToMap:
             raise ValueError("exchange must be 'nccl' or 'peer'")
 
     def search(self, stream=None):
-        """records <- exact nearest point of this shard for the current scan state."""
-        rc = _lib().b200icp_s2m_search(C.byref(self.shard.desc), _ptr(self.src64), self.n,
+        """records <- exact nearest point of this shard for the current scan state (or "none" for
+        points whose nearest neighbour is provably in another rank's shard)."""
+        import torch.distributed as dist
+        rc = _lib().b200icp_s2m_bound(C.byref(self.shard.desc), _ptr(self.src64), self.n, _ptr(self.ub),
+                                      _ptr(self.state), _stream_ptr(stream))
+        _cabi.check(rc, "b200icp_s2m_bound")
+        if self.world > 1:             # global bound: 4 bytes per scan point
+            dist.all_reduce(self.ub, op=dist.ReduceOp.MIN, group=self.group)
+        rc = _lib().b200icp_s2m_search(C.byref(self.shard.desc), _ptr(self.src64), self.n, _ptr(self.ub),
                                        _ptr(self.records), _ptr(self.workspace),
                                        self.workspace.numel(), _ptr(self.state), _stream_ptr(stream))
         _cabi.check(rc, "b200icp_s2m_search")
@@ -241,7 +250,7 @@ class ScanToMapLocalShards:
     several GPUs.  ``step()`` runs one iteration so callers can inspect per-iteration state."""
 
     def __init__(self, shards, n_scan: int, want_indices: bool = True):
-        self.workers = [ScanToMap(s, n_scan) for s in shards]
+        self.workers = [ScanToMap(s, n_scan, local_only=True) for s in shards]
         self.n, self.dev = int(n_scan), shards[0].points.device
         w0 = self.workers[0]
         self.src64, self.state = w0.src64, w0.state
@@ -257,11 +266,18 @@ class ScanToMapLocalShards:
         _cabi.check(rc, "b200icp_s2m_init")
 
     def step(self, max_iterations: int, tolerance: float, max_corr_dist=None):
+        for w in self.workers:         # per-shard bounds, then the "all-reduce": elementwise min
+            rc = _lib().b200icp_s2m_bound(C.byref(w.shard.desc), _ptr(self.src64), self.n, _ptr(w.ub),
+                                          _ptr(self.state), _stream_ptr(None))
+            _cabi.check(rc, "b200icp_s2m_bound")
+        ub = self.workers[0].ub
+        for w in self.workers[1:]:
+            torch.minimum(ub, w.ub, out=ub)
         for g, w in enumerate(self.workers):
             rec = self.records_all[g]
-            rc = _lib().b200icp_s2m_search(C.byref(w.shard.desc), _ptr(self.src64), self.n, _ptr(rec),
-                                           _ptr(w.workspace), w.workspace.numel(), _ptr(self.state),
-                                           _stream_ptr(None))
+            rc = _lib().b200icp_s2m_search(C.byref(w.shard.desc), _ptr(self.src64), self.n, _ptr(ub),
+                                           _ptr(rec), _ptr(w.workspace), w.workspace.numel(),
+                                           _ptr(self.state), _stream_ptr(None))
             _cabi.check(rc, "b200icp_s2m_search")
         rc = _lib().b200icp_s2m_update(_ptr(self.records_all), len(self.workers), _ptr(self.src64),
                                        self.n, int(max_iterations), float(tolerance),

@@ -154,7 +154,10 @@ int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_
  * contiguously across GPUs (one process per GPU).  The scan-to-local-map call shape of
  * duc/ICP_LIDAR/mainn.py:297-318 / slam_offline.py:366-392 with the point-to-point loop of
  * labels_segmentation/icp.py:28-53.  Per iteration and rank:
+ *     b200icp_s2m_bound   -> ub[n]        upper bound of every point's NN distance to this shard
+ *     (caller)               min-reduce of ub across ranks (32 KB)
  *     b200icp_s2m_search  -> records[n]   exact nearest map point of THIS shard per scan point
+ *                                          (or "none" when the shard is out of reach of the point)
  *     (caller)               all-gather of the records of every rank  -> records_all[ranks][n]
  *     b200icp_s2m_update  -> global winner per point (distance, then lowest global index),
  *                            pose solve, apply, convergence; bit-identical on every rank.
@@ -194,9 +197,15 @@ int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream);
 /* src64 [n][2] float64 scan state (written), state (written) */
 int b200icp_s2m_init(const void* scan, int32_t dtype, int32_t n, const double* init_pose /*[6]|NULL*/,
                      double* src64, b200icp_s2m_state* state, void* stream);
+/* ub[n] float32: per scan point an upper bound of its NN distance to THIS shard (min over chunk
+ * centres of distance + radius).  With several ranks the caller min-reduces ub across ranks
+ * before the search, so that a rank sweeps only the chunks that can hold a GLOBAL winner. */
+int b200icp_s2m_bound(const b200icp_s2m_shard* shard, const double* src64, int32_t n, float* ub,
+                      const b200icp_s2m_state* state, void* stream);
+/* records[i].d2 = +inf when no chunk of this shard is within ub[i] of point i's tile. */
 int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int32_t n,
-                       b200icp_s2m_record* records, void* workspace, int64_t workspace_bytes,
-                       const b200icp_s2m_state* state, void* stream);
+                       const float* ub, b200icp_s2m_record* records, void* workspace,
+                       int64_t workspace_bytes, const b200icp_s2m_state* state, void* stream);
 int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, double* src64,
                        int32_t n, int32_t max_iterations, double tolerance, double max_corr_dist,
                        int32_t* idx_out /*[n]|NULL*/, b200icp_s2m_state* state, void* stream);
