@@ -162,7 +162,12 @@ __global__ void __launch_bounds__(256) s2m_prepare_kernel(const void* points, in
 //          point's nearest neighbour, so it can be neither the winner nor a tie: results are
 //          identical to the full sweep.  Kept chunks are written as an ordered list per tile.
 // ------------------------------------------------------------------------------------------
-constexpr int kSegChunks = 8;         // listed chunks per sweep CTA
+constexpr int kItemsPerTile = 256;    // sweep CTAs per tile of 512 scan points (grid.x)
+// listed chunks per sweep CTA: the tile's kept chunks are spread evenly over kItemsPerTile CTAs
+__host__ __device__ inline int seg_chunks_for(int kept) {
+  const int s = (kept + kItemsPerTile - 1) / kItemsPerTile;
+  return s < 1 ? 1 : s;
+}
 constexpr float kSqrt2Up = 1.4142137f;
 
 constexpr int kBoundChunks = 256;     // chunk origins staged per CTA of the bound kernel
@@ -274,7 +279,8 @@ __global__ void __launch_bounds__(kSweepThreads) s2m_sweep_kernel(
   const int tid = threadIdx.x;
   const int item = blockIdx.x, tile = blockIdx.y;
   const int kept = tile_count[tile];
-  const int c0 = item * kSegChunks, c1 = min(kept, c0 + kSegChunks);   // positions in the tile's list
+  const int seg = seg_chunks_for(kept);
+  const int c0 = item * seg, c1 = min(kept, c0 + seg);                 // positions in the tile's list
   if (c0 >= c1) return;
   const int32_t* __restrict__ list = tile_list + (int64_t)tile * n_chunks;
 
@@ -386,14 +392,25 @@ __global__ void __launch_bounds__(128) s2m_resolve_kernel(
   if (i >= n) return;
   float g_ub = CUDART_INF_F, g_lb1 = CUDART_INF_F, g_lb2 = CUDART_INF_F;
   uint32_t where = 0;
-  const int n_items = (tile_count[i / kSrcPerCta] + kSegChunks - 1) / kSegChunks;
+  const int kept = tile_count[i / kSrcPerCta];
+  const int seg_chunks = seg_chunks_for(kept);
+  const int n_items = (kept + seg_chunks - 1) / seg_chunks;
   if (n_items == 0) {            // every chunk of this shard is out of reach: another rank holds the NN
     b200icp_s2m_record none;
     none.d2 = CUDART_INF; none.gidx = 0x7fffffffffffffffLL; none.bx = 0.0; none.by = 0.0;
     records[i] = none;
     return;
   }
-  for (int s = 0; s < n_items; ++s) {
+  int s = 0;
+  for (; s + 4 <= n_items; s += 4) {          // four independent loads in flight per trip
+    const Partial p0 = partials[(int64_t)s * n + i], p1 = partials[(int64_t)(s + 1) * n + i];
+    const Partial p2 = partials[(int64_t)(s + 2) * n + i], p3 = partials[(int64_t)(s + 3) * n + i];
+    merge_partial(g_ub, g_lb1, g_lb2, where, p0.ub, p0.lb1, p0.lb2, p0.where);
+    merge_partial(g_ub, g_lb1, g_lb2, where, p1.ub, p1.lb1, p1.lb2, p1.where);
+    merge_partial(g_ub, g_lb1, g_lb2, where, p2.ub, p2.lb1, p2.lb2, p2.where);
+    merge_partial(g_ub, g_lb1, g_lb2, where, p3.ub, p3.lb1, p3.lb2, p3.where);
+  }
+  for (; s < n_items; ++s) {
     const Partial p = partials[(int64_t)s * n + i];
     merge_partial(g_ub, g_lb1, g_lb2, where, p.ub, p.lb1, p.lb2, p.where);
   }
@@ -714,7 +731,7 @@ Workspace layout_workspace(int n, int64_t m) {
   Workspace w;
   const int64_t n_chunks = (m + kChunk - 1) / kChunk;
   w.tiles = (n + kSrcPerCta - 1) / kSrcPerCta;
-  w.n_items = (int)((n_chunks + kSegChunks - 1) / kSegChunks);
+  w.n_items = (int)(n_chunks < kItemsPerTile ? n_chunks : kItemsPerTile);
   int64_t off = 256;                                         // [0]: ambiguous-source counter
   w.amb_list = off;   off += up((int64_t)n * 4);
   w.tile_count = off; off += up((int64_t)w.tiles * 4);
