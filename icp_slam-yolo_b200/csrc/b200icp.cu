@@ -650,9 +650,8 @@ struct WarpTile {
   const void* tgt;      // global target table
   int64_t row_off;      // first point of this pair's target row
   int dtype;
-  float* fx;            // [mcap] centred float32 x
-  float* fy;            // [mcap]
-  float* ft;            // [mcap] |centred|^2, +inf sentinels
+  float* tile;          // [mcap/8][24]: per group of 8 targets x[8], y[8], |t|^2[8] (centred float32),
+                        // 96 contiguous bytes = six LDS.128 off one address
   double2* src;         // [ncap] float64 source state
   float* gcx;           // [mcap/8] bounding circle of each group of 8 targets (pruned sweep)
   float* gcy;
@@ -691,7 +690,8 @@ __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
       tt = (float)((double)cx * (double)cx + (double)cy * (double)cy);
       amax = fmaxf(amax, fmaxf(fabsf(cx), fabsf(cy)));
     }
-    t.fx[j] = cx; t.fy[j] = cy; t.ft[j] = tt;
+    float* gq = t.tile + (j >> 3) * 24 + (j & 7);
+    gq[0] = cx; gq[8] = cy; gq[16] = tt;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
@@ -703,8 +703,9 @@ __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
     for (int u = 0; u < kGroup; ++u) {
       const int j = g * kGroup + u;
       if (j < t.m) {
-        x0 = fminf(x0, t.fx[j]); x1 = fmaxf(x1, t.fx[j]);
-        y0 = fminf(y0, t.fy[j]); y1 = fmaxf(y1, t.fy[j]);
+        const float px = t.tile[g * 24 + u], py = t.tile[g * 24 + 8 + u];
+        x0 = fminf(x0, px); x1 = fmaxf(x1, px);
+        y0 = fminf(y0, py); y1 = fmaxf(y1, py);
       }
     }
     const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
@@ -712,7 +713,7 @@ __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
     for (int u = 0; u < kGroup; ++u) {
       const int j = g * kGroup + u;
       if (j < t.m) {
-        const float dx = t.fx[j] - cx, dy = t.fy[j] - cy;
+        const float dx = t.tile[g * 24 + u] - cx, dy = t.tile[g * 24 + 8 + u] - cy;
         r2 = fmaxf(r2, fmaf(dx, dx, dy * dy));
       }
     }
@@ -727,9 +728,7 @@ __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
 template <int S>
 __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (&sx)[S],
                                                 const float (&sy)[S], Candidates<S>& c) {
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
-  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
-  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(t.ft);
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile);
   float a[S], b[S];
 #pragma unroll
   for (int k = 0; k < S; ++k) {
@@ -741,9 +740,9 @@ __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (
   const int ngroups = t.ngroups;
 #pragma unroll 1
   for (int g = 0; g < ngroups; ++g) {
-    const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
-    const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
-    const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
+    const float4 xa = g4[6 * g], xb = g4[6 * g + 1];
+    const float4 ya = g4[6 * g + 2], yb = g4[6 * g + 3];
+    const float4 qa = g4[6 * g + 4], qb = g4[6 * g + 5];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
@@ -766,13 +765,11 @@ struct GroupRegs {
 };
 
 __device__ __forceinline__ GroupRegs load_group(const WarpTile& t, int g) {
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
-  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
-  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(t.ft);
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * g;
   GroupRegs r;
-  r.xa = x4[2 * g]; r.xb = x4[2 * g + 1];
-  r.ya = y4[2 * g]; r.yb = y4[2 * g + 1];
-  r.qa = q4[2 * g]; r.qb = q4[2 * g + 1];
+  r.xa = g4[0]; r.xb = g4[1];
+  r.ya = g4[2]; r.yb = g4[3];
+  r.qa = g4[4]; r.qb = g4[5];
   return r;
 }
 
@@ -823,15 +820,6 @@ __device__ __forceinline__ void eval_mask(const WarpTile& t, unsigned mask, int 
 #endif
 }
 
-// Pruned candidate sweep.  The 32*S sources of a pass are consecutive scan points, i.e. a short
-// piece of wall; their bounding circle is compared with the bounding circle of every group of
-// 8 targets.  Stage A evaluates the groups whose circles overlap the sources' circle; that
-// yields, per source, an upper bound of its nearest-neighbour distance.  Stage B evaluates
-// every remaining group whose circle could still hold a point within (that bound + the
-// ambiguity margin) of any source.  Every skipped group is PROVEN farther than best + margin
-// for every source of the pass, so the tracked best / runner-up / group are exactly what the
-// full sweep would have produced for the purposes of nn-resolution (DESIGN.md 4.1); on
-// unordered inputs every group overlaps and this degenerates to the full sweep.
 // Warp-wide min / max of a float through the integer REDUX unit (one instruction instead of a
 // five-step shuffle tree): floats are mapped to order-preserving unsigned keys first.
 __device__ __forceinline__ unsigned f32_ordered(float f) {
@@ -855,6 +843,15 @@ __device__ __forceinline__ float box_dist2(float px, float py, float x0, float x
   return fmaf(dx, dx, dy * dy);
 }
 
+// Pruned candidate sweep.  The 32*S sources of a pass are consecutive scan points, i.e. a short
+// piece of wall; their bounding box is compared with the bounding circle of every group of
+// 8 targets.  Stage A evaluates the groups whose circles touch the sources' box; that
+// yields, per source, an upper bound of its nearest-neighbour distance.  Stage B evaluates
+// every remaining group whose circle could still hold a point within (that bound + the
+// ambiguity margin) of any source.  Every skipped group is PROVEN farther than best + margin
+// for every source of the pass, so the tracked best / runner-up / group are exactly what the
+// full sweep would have produced for the purposes of nn-resolution (DESIGN.md 4.1); on
+// unordered inputs every group overlaps and this degenerates to the full sweep.
 template <int S>
 __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
                                                       const float (&sy)[S], const bool (&valid)[S],
@@ -935,10 +932,9 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
 // whether a runner-up lies inside the guard band.
 __device__ __forceinline__ int in_group_argmin(const WarpTile& t, int g, float fx, float fy,
                                                bool& near_tie) {
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
-  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(t.fy);
-  const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
-  const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * g;
+  const float4 xa = g4[0], xb = g4[1];
+  const float4 ya = g4[2], yb = g4[3];
   const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
   const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
   unsigned best = 0x7f800000u, second = 0x7f800000u;       // +inf as ordered bit patterns
@@ -986,10 +982,8 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
   WarpTile t;
   t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
   t.mcap = a.mcap; t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
-  t.fx = reinterpret_cast<float*>(smem_raw);
-  t.fy = t.fx + a.mcap;
-  t.ft = t.fy + a.mcap;
-  t.src = reinterpret_cast<double2*>(t.ft + a.mcap);       // 12*mcap bytes, mcap % 8 == 0
+  t.tile = reinterpret_cast<float*>(smem_raw);
+  t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);  // 12*mcap bytes, mcap % 8 == 0
   WarpCtx* ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
   t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + 160);
   t.gcy = t.gcx + a.mcap / kGroup;
