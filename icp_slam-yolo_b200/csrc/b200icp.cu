@@ -935,14 +935,19 @@ __device__ __forceinline__ int in_group_argmin(const WarpTile& t, int g, float f
   const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * g;
   const float4 xa = g4[0], xb = g4[1];
   const float4 ya = g4[2], yb = g4[3];
-  const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-  const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+  // direct differences, two targets per packed instruction (the sign of dx, dy is irrelevant)
+  const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy);
+  const float2 u0 = __fadd2_rn(make_float2(xa.x, xa.y), nx), v0 = __fadd2_rn(make_float2(ya.x, ya.y), ny);
+  const float2 u1 = __fadd2_rn(make_float2(xa.z, xa.w), nx), v1 = __fadd2_rn(make_float2(ya.z, ya.w), ny);
+  const float2 u2 = __fadd2_rn(make_float2(xb.x, xb.y), nx), v2 = __fadd2_rn(make_float2(yb.x, yb.y), ny);
+  const float2 u3 = __fadd2_rn(make_float2(xb.z, xb.w), nx), v3 = __fadd2_rn(make_float2(yb.z, yb.w), ny);
+  const float2 d01 = __ffma2_rn(v0, v0, __fmul2_rn(u0, u0)), d23 = __ffma2_rn(v1, v1, __fmul2_rn(u1, u1));
+  const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
+  const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
   unsigned best = 0x7f800000u, second = 0x7f800000u;       // +inf as ordered bit patterns
 #pragma unroll
   for (int u = 0; u < kGroup; ++u) {
-    const float dx = fx - xs[u], dy = fy - ys[u];
-    const float d = fmaf(dy, dy, dx * dx);                   // sentinel slots: ~2e36, never win
-    const unsigned key = (__float_as_uint(d) & ~7u) | (unsigned)u;   // d >= 0: bits are ordered
+    const unsigned key = (__float_as_uint(ds[u]) & ~7u) | (unsigned)u;   // d >= 0: bits are ordered
     second = min(second, max(best, key));
     best = min(best, key);
   }
