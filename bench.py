@@ -340,9 +340,9 @@ def run_b200(args):
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                      "peak_source": "b200icp_ffma_probe measured live (dependent-FFMA chains, all SMs)",
                      "algorithmic_flop_per_launch": flops, "kernel_ms": kernel_ms,
-                     "traffic": 389971968 if P == 65536 else None,
+                     "traffic": 391111168 if P == 65536 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                       "capture profiles/r1f_align_pruned_ncu_details.txt (algorithmic: 380.6 MB)",
+                                       "capture profiles/r1g_align_pruned_final_ncu.txt (algorithmic: 380.6 MB)",
                      "executed_pair_eval_fraction": executed / (P * PAIR_EVALS_PER_ALIGNMENT),
                      "executed_tflops": executed * FLOP_PER_PAIR_EVAL / (kernel_ms * 1e-3) / 1e12,
                      "dense_sweep": {"kernel": "icp_align_warp_kernel<6,dense> (B200ICP_PRUNE=0: every pair-eval "
