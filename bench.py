@@ -275,18 +275,16 @@ def run_b200(args):
     del stats
     # untimed-for-the-headline A/B: the dense (no pruning) sweep of the same kernel, i.e. the
     # brute-force FP32 roofline number; identical results required
-    os.environ["B200ICP_PRUNE"] = "0"
     dense_out = m.alloc_outputs(P, N_POINTS, dev)
     for _ in range(2):
-        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, out=dense_out)
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, dense_sweep=True, out=dense_out)
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d0.record()
     for _ in range(3):
-        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, out=dense_out)
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, dense_sweep=True, out=dense_out)
     d1.record()
     torch.cuda.synchronize()
     dense_ms = d0.elapsed_time(d1) / 3
-    os.environ.pop("B200ICP_PRUNE")
     assert torch.equal(dense_out.pose_total, out.pose_total), "dense and pruned sweeps disagree"
     del dense_out
 
@@ -345,7 +343,7 @@ def run_b200(args):
                                        "capture profiles/r1g_align_pruned_final_ncu.txt (algorithmic: 380.6 MB)",
                      "executed_pair_eval_fraction": executed / (P * PAIR_EVALS_PER_ALIGNMENT),
                      "executed_tflops": executed * FLOP_PER_PAIR_EVAL / (kernel_ms * 1e-3) / 1e12,
-                     "dense_sweep": {"kernel": "icp_align_warp_kernel<6,dense> (B200ICP_PRUNE=0: every pair-eval "
+                     "dense_sweep": {"kernel": "icp_align_warp_kernel<6,dense> (B200ICP_FLAG_DENSE_SWEEP: every pair-eval "
                                                "executed; bit-identical poses)", "kernel_ms": dense_ms,
                                      "achieved": flops / (dense_ms * 1e-3) / 1e12,
                                      "frac": flops / (dense_ms * 1e-3) / 1e12 / fp32_peak},

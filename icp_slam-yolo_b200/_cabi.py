@@ -16,6 +16,7 @@ c_f64p = C.POINTER(C.c_double)
 OK = 0
 F32, F64 = 0, 1
 PAIR_ROWWISE, PAIR_EXPLICIT, PAIR_TRIANGLE = 0, 1, 2
+FLAG_DENSE_SWEEP = 1
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "CUDA", 4: "NO_DEVICE"}
 
@@ -33,7 +34,7 @@ class Problem(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [
-        ("max_iterations", C.c_int32), ("reserved", C.c_int32),
+        ("max_iterations", C.c_int32), ("flags", C.c_int32),
         ("tolerance", C.c_double), ("max_corr_dist", C.c_double),
         ("init_pose", C.c_void_p),
     ]

@@ -1589,7 +1589,7 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
     LaunchShape ws = ls;
     ws.warps = 1;
     ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
-    if (env_int("B200ICP_PRUNE", 1) != 0) {
+    if (env_int("B200ICP_PRUNE", 1) != 0 && !(opt->flags & B200ICP_FLAG_DENSE_SWEEP)) {
       // pruned sweep: passes of 64 consecutive sources (2 per lane)
       int SP = env_int("B200ICP_PRUNE_S", 2);
       if (SP < 1 || SP > 4) SP = 2;

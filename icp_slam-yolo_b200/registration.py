@@ -210,12 +210,15 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
                 max_iterations: int = 20, tolerance: float = 1e-5,
                 init_pose: Optional[torch.Tensor] = None, max_corr_dist: Optional[float] = None,
                 want_indices: bool = False, want_src: bool = False, want_history: bool = False,
-                want_stats: bool = False, out: Optional[AlignResult] = None, stream=None) -> AlignResult:
+                want_stats: bool = False, dense_sweep: bool = False,
+                out: Optional[AlignResult] = None, stream=None) -> AlignResult:
     """Run the whole ICP loop of every pair on the device (one kernel launch).
 
     Replaces ``icp(A, B, max_iterations, tolerance)`` (icp.py:28-53) for a batch:
     same defaults, same convergence rule, same lagged error.  ``init_pose`` is
     [B,6] float64 (R row-major, t); ``max_corr_dist`` None = exactly the reference.
+    ``dense_sweep`` evaluates every source-target pair instead of culling target groups that are
+    provably out of reach (identical results; only worth it for spatially unordered point sets).
     """
     pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
     b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
@@ -226,6 +229,7 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
                             want_stats=want_stats)
     opt = _cabi.Options()
     opt.max_iterations = int(max_iterations)
+    opt.flags = _cabi.FLAG_DENSE_SWEEP if dense_sweep else 0
     opt.tolerance = float(tolerance)
     opt.max_corr_dist = 0.0 if max_corr_dist is None else float(max_corr_dist)
     if init_pose is not None:

@@ -438,3 +438,13 @@ def test_host_pipeline_matches_resident_path(b200, cart_scans):
     pose2, _, _ = pipe.run(hs, ht, hsl, htl, max_iterations=30, tolerance=1e-5)      # buffers are reusable
     torch.cuda.synchronize()
     assert torch.equal(pose2, ref.pose_total.cpu())
+
+
+def test_dense_sweep_flag_gives_identical_bits(b200, cart_scans):
+    table = b200.ScanTable.from_list(cart_scans[900:964])
+    a = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5, want_indices=True, want_stats=True)
+    d = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5, want_indices=True, want_stats=True,
+                               dense_sweep=True)
+    assert torch.equal(a.pose_total, d.pose_total) and torch.equal(a.indices, d.indices)
+    assert torch.equal(a.iterations, d.iterations) and torch.equal(a.error, d.error)
+    assert int(a.evaluated_pairs.sum()) < int(d.evaluated_pairs.sum())      # something was culled
