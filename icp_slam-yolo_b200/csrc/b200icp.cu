@@ -959,6 +959,7 @@ __device__ __forceinline__ int in_group_argmin(const WarpTile& t, int g, float f
   return (int)(best & 7u);
 }
 
+
 // Per-pair state that is touched once per iteration lives in shared memory, not registers:
 // the sweep needs ~5 registers per source point and every long-lived double evicted from the
 // register file is one more independent FFMA2/FMNMX chain the scheduler can keep in flight.
@@ -969,6 +970,138 @@ struct WarpCtx {
   double inv_n;
   int iters, inl;
 };
+
+// One pass of the correspondence search: the exact nearest target index j[k] for the SC source
+// points (base + k*32 + lane) of every lane, read from the float64 source state in shared memory.
+// Candidate sweep (FP32, pruned or dense) -> FP32 in-group argmin -> guards -> rare
+// warp-cooperative float64 rescans.  Returns the pair evaluations the sweep executed.
+template <int SC, bool PRUNE>
+__device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int base, int n, int m,
+                                                      int lane, int (&j)[SC]) {
+  long long evals = 0;
+  float fx[SC], fy[SC];
+#pragma unroll
+  for (int k = 0; k < SC; ++k) {
+    const double2 s = t.src[base + k * 32 + lane];
+    fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
+  }
+  Candidates<SC> c;
+  if (PRUNE) {
+    bool vld[SC];
+#pragma unroll
+    for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
+    const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c);
+    evals += (long long)groups * kGroup * min(32 * SC, n - base);
+  } else {
+    warp_candidates<SC>(t, fx, fy, c);
+    evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
+  }
+  bool amb[SC];
+  bool any_amb = false;
+#pragma unroll
+  for (int k = 0; k < SC; ++k) {
+    bool tie_in;
+    const int slot = in_group_argmin(t, c.group[k], fx[k], fy[k], tie_in);
+    j[k] = c.group[k] * kGroup + slot;
+    amb[k] = (base + k * 32 + lane < n) &&
+             (tie_in || is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax));
+    any_amb |= amb[k];
+  }
+  if (__any_sync(kFull, any_amb)) {      // rare: warp-cooperative float64 scan
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      unsigned pending = __ballot_sync(kFull, amb[k]);
+      if (!pending) continue;
+      const double2 s = t.src[base + k * 32 + lane];
+      int jk = j[k];
+      while (pending) {
+        const int owner = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const double qx = __shfl_sync(kFull, s.x, owner), qy = __shfl_sync(kFull, s.y, owner);
+        double ld = CUDART_INF;
+        int lj = 0x7fffffff;
+        for (int jj = lane; jj < m; jj += 32) {
+          const double d = dist2_f64(qx, qy, load_point(t.tgt, t.dtype, t.row_off + jj));
+          if (d < ld) { ld = d; lj = jj; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(kFull, ld, o);
+          const int oj = __shfl_xor_sync(kFull, lj, o);
+          if (od < ld || (od == ld && oj < lj)) { ld = od; lj = oj; }
+        }
+        if (lane == owner) jk = lj;
+      }
+      j[k] = jk;
+    }
+  }
+  return evals;
+}
+
+// Warp-per-pair tile set-up shared by the fused loop and the search-only kernel.
+__device__ __forceinline__ void carve_warp_tile(unsigned char* smem, const KernelArgs& a, WarpTile& t,
+                                                WarpCtx*& ctx) {
+  t.mcap = a.mcap;
+  t.tile = reinterpret_cast<float*>(smem);
+  t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);  // 12*mcap bytes, mcap % 8 == 0
+  ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
+  t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + 160);
+  t.gcy = t.gcx + a.mcap / kGroup;
+  t.grad = t.gcy + a.mcap / kGroup;
+}
+
+// ------------------------------------------------------------------------------------
+// kernel: correspondence search only, one warp per pair (icp.py:37-38): same tile, sweep and
+// exact re-decision as the fused loop, one search, outputs idx and the exact float64 d^2.
+// ------------------------------------------------------------------------------------
+template <int SC, bool PRUNE>
+__global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) nn_warp_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int64_t p = blockIdx.x;
+  const b200icp_problem& pr = a.prob;
+  int64_t srow, trow;
+  resolve_rows(pr, p, srow, trow);
+  const int n = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
+  const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
+  int32_t* idx_out = a.nn_idx + p * pr.src_pitch;
+  double* d2_out = a.nn_dist2 ? a.nn_dist2 + p * pr.src_pitch : nullptr;
+  if (n <= 0 || m <= 0) {
+    for (int i = lane; i < pr.src_pitch; i += 32) {
+      idx_out[i] = -1;
+      if (d2_out) d2_out[i] = CUDART_INF;
+    }
+    return;
+  }
+  WarpTile t;
+  WarpCtx* ctx;
+  carve_warp_tile(smem_raw, a, t, ctx);
+  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
+  t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
+  warp_stage_targets(t, lane);
+  for (int i = lane; i < a.ncap; i += 32)
+    t.src[i] = i < n ? load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i) : make_double2(t.ox, t.oy);
+  __syncwarp();
+  for (int base = 0; base < n; base += 32 * SC) {
+    int j[SC];
+    warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j);
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      const int i = base + k * 32 + lane;
+      if (i < n) {
+        idx_out[i] = j[k];
+        if (d2_out) {
+          const double2 s = t.src[i];
+          d2_out[i] = dist2_f64(s.x, s.y, load_point(t.tgt, t.dtype, t.row_off + j[k]));
+        }
+      }
+    }
+  }
+  for (int i = n + lane; i < pr.src_pitch; i += 32) {
+    idx_out[i] = -1;
+    if (d2_out) d2_out[i] = CUDART_INF;
+  }
+}
 
 template <int SC, bool PRUNE>
 __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_kernel(const KernelArgs a) {
@@ -985,14 +1118,10 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
   const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
 
   WarpTile t;
+  WarpCtx* ctx;
+  carve_warp_tile(smem_raw, a, t, ctx);
   t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
-  t.mcap = a.mcap; t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
-  t.tile = reinterpret_cast<float*>(smem_raw);
-  t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);  // 12*mcap bytes, mcap % 8 == 0
-  WarpCtx* ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
-  t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + 160);
-  t.gcy = t.gcx + a.mcap / kGroup;
-  t.grad = t.gcy + a.mcap / kGroup;
+  t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
 
   const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
   if (lane == 0) {
@@ -1032,66 +1161,9 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
           ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
       double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int base = 0; base < n; base += 32 * SC) {
-        // ---- candidate sweep for SC sources per lane (icp.py:37-38)
-        float fx[SC], fy[SC];
-#pragma unroll
-        for (int k = 0; k < SC; ++k) {
-          const double2 s = t.src[base + k * 32 + lane];
-          fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
-        }
-        Candidates<SC> c;
-        if (PRUNE) {
-          bool vld[SC];
-#pragma unroll
-          for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
-          const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c);
-          evals += (long long)groups * kGroup * min(32 * SC, n - base);
-        } else {
-          warp_candidates<SC>(t, fx, fy, c);
-          evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
-        }
-        // ---- exact decision in three straight-line phases so the SC matched-point loads
-        //      (global, L1/L2) and the SC float64 sqrt chains overlap instead of serialising
+        // ---- correspondence search for the SC sources of every lane (icp.py:37-38)
         int j[SC];
-        bool amb[SC];
-        bool any_amb = false;
-#pragma unroll
-        for (int k = 0; k < SC; ++k) {
-          bool tie_in;
-          const int slot = in_group_argmin(t, c.group[k], fx[k], fy[k], tie_in);
-          j[k] = c.group[k] * kGroup + slot;
-          amb[k] = (base + k * 32 + lane < n) &&
-                   (tie_in || is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax));
-          any_amb |= amb[k];
-        }
-        if (__any_sync(kFull, any_amb)) {      // rare: warp-cooperative float64 scan
-#pragma unroll
-          for (int k = 0; k < SC; ++k) {
-            unsigned pending = __ballot_sync(kFull, amb[k]);
-            if (!pending) continue;
-            const double2 s = t.src[base + k * 32 + lane];
-            int jk = j[k];
-            while (pending) {
-              const int owner = __ffs(pending) - 1;
-              pending &= pending - 1;
-              const double qx = __shfl_sync(kFull, s.x, owner), qy = __shfl_sync(kFull, s.y, owner);
-              double ld = CUDART_INF;
-              int lj = 0x7fffffff;
-              for (int jj = lane; jj < m; jj += 32) {
-                const double d = dist2_f64(qx, qy, load_point(t.tgt, t.dtype, t.row_off + jj));
-                if (d < ld) { ld = d; lj = jj; }
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                const double od = __shfl_xor_sync(kFull, ld, o);
-                const int oj = __shfl_xor_sync(kFull, lj, o);
-                if (od < ld || (od == ld && oj < lj)) { ld = od; lj = oj; }
-              }
-              if (lane == owner) jk = lj;
-            }
-            j[k] = jk;
-          }
-        }
+        evals += warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j);
         // ---- gather (icp.py:39): all SC loads in flight before the first use
         double2 bm[SC];
 #pragma unroll
@@ -1501,6 +1573,66 @@ int launch_pairs(Kern kern, const LaunchShape& ls, const KernelArgs& args, cudaS
   return B200ICP_OK;
 }
 
+// Warp-per-pair launch shape: the pruned sweep works in passes of 32*SP consecutive sources
+// (SP = 2), the dense sweep in passes of 32*SC sources chosen to minimise padding.
+struct WarpShape {
+  int S;
+  bool prune;
+};
+
+WarpShape pick_warp_shape(const b200icp_problem* prob, bool dense, const LaunchShape& ls, KernelArgs& args,
+                          LaunchShape& ws) {
+  WarpShape w;
+  w.prune = !dense;
+  if (w.prune) {
+    w.S = env_int("B200ICP_PRUNE_S", 2);
+    if (w.S < 1 || w.S > 4) w.S = 2;
+  } else {
+    w.S = env_int("B200ICP_FORCE_SC", 0);
+    if (w.S != 2 && w.S != 4 && w.S != 6 && w.S != 8 && w.S != 12) {
+      // cost model: padded source slots, plus a per-sweep overhead that shrinks with the pass
+      // width (target LDS and loop control are shared by the SC sources of a lane).  SC = 12 is
+      // compiled but never chosen: one 12-wide pass measured slower than two 6-wide passes on
+      // B200 (profiles/r1_kernel_tuning.md).
+      const int cand[4] = {8, 6, 4, 2};
+      double best_cost = 1e30;
+      w.S = 8;
+      for (int q = 0; q < 4; ++q) {
+        const int span = 32 * cand[q];
+        const int slots = (prob->src_pitch + span - 1) / span * span;
+        const double cost = slots * (1.0 + 1.0 / cand[q]);
+        if (cost < best_cost) { best_cost = cost; w.S = cand[q]; }
+      }
+    }
+  }
+  args.ncap = (prob->src_pitch + 32 * w.S - 1) / (32 * w.S) * (32 * w.S);
+  ws = ls;
+  ws.warps = 1;
+  ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
+  return w;
+}
+
+#define B200ICP_DISPATCH_WARP(KERNEL, DENSE)                                             \
+  {                                                                                      \
+    LaunchShape ws;                                                                      \
+    const WarpShape w = pick_warp_shape(prob, DENSE, ls, args, ws);                      \
+    if (w.prune) {                                                                       \
+      switch (w.S) {                                                                     \
+        case 1: return launch_pairs(KERNEL<1, true>, ws, args, st);                      \
+        case 2: return launch_pairs(KERNEL<2, true>, ws, args, st);                      \
+        case 3: return launch_pairs(KERNEL<3, true>, ws, args, st);                      \
+        default: return launch_pairs(KERNEL<4, true>, ws, args, st);                     \
+      }                                                                                  \
+    }                                                                                    \
+    switch (w.S) {                                                                       \
+      case 2: return launch_pairs(KERNEL<2, false>, ws, args, st);                       \
+      case 4: return launch_pairs(KERNEL<4, false>, ws, args, st);                       \
+      case 6: return launch_pairs(KERNEL<6, false>, ws, args, st);                       \
+      case 8: return launch_pairs(KERNEL<8, false>, ws, args, st);                       \
+      default: return launch_pairs(KERNEL<12, false>, ws, args, st);                     \
+    }                                                                                    \
+  }
+
 }  // namespace
 
 // shared with scan2map.cu (C++ linkage: not part of the C ABI)
@@ -1542,6 +1674,10 @@ int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs, int32_t* idx_
     case 8: return launch_pairs(KERNEL<4, false>, ls, args, st);                       \
     default: return launch_pairs(KERNEL<4, true>, ls, args, st);                       \
   }
+  if (env_int("B200ICP_NN_BLOCK", 0) == 0) {
+    const bool dense = env_int("B200ICP_PRUNE", 1) == 0;
+    B200ICP_DISPATCH_WARP(nn_warp_kernel, dense)
+  }
   B200ICP_DISPATCH(nn_pair_kernel)
 }
 
@@ -1568,47 +1704,8 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   args.use_gate = (opt->max_corr_dist > 0.0 && std::isfinite(opt->max_corr_dist)) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (env_int("B200ICP_ALIGN_BLOCK", 0) == 0) {
-    // warp-per-pair kernel: SC sources per lane per sweep, one-warp CTAs
-    int SC = env_int("B200ICP_FORCE_SC", 0);
-    if (SC != 2 && SC != 4 && SC != 6 && SC != 8 && SC != 12) {
-      // cost model: padded source slots, plus a per-sweep overhead that shrinks with the
-      // pass width (target LDS and loop control are shared by the SC sources of a lane).
-      // SC = 12 is compiled but never chosen: one 12-wide pass measured slower than two
-      // 6-wide passes on B200 (profiles/r1_kernel_tuning.md).
-      const int cand[4] = {8, 6, 4, 2};
-      double best_cost = 1e30;
-      SC = 8;
-      for (int q = 0; q < 4; ++q) {
-        const int span = 32 * cand[q];
-        const int slots = (prob->src_pitch + span - 1) / span * span;
-        const double cost = slots * (1.0 + 1.0 / cand[q]);
-        if (cost < best_cost) { best_cost = cost; SC = cand[q]; }
-      }
-    }
-    args.ncap = (prob->src_pitch + 32 * SC - 1) / (32 * SC) * (32 * SC);
-    LaunchShape ws = ls;
-    ws.warps = 1;
-    ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
-    if (env_int("B200ICP_PRUNE", 1) != 0 && !(opt->flags & B200ICP_FLAG_DENSE_SWEEP)) {
-      // pruned sweep: passes of 64 consecutive sources (2 per lane)
-      int SP = env_int("B200ICP_PRUNE_S", 2);
-      if (SP < 1 || SP > 4) SP = 2;
-      args.ncap = (prob->src_pitch + 32 * SP - 1) / (32 * SP) * (32 * SP);
-      ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
-      switch (SP) {
-        case 1: return launch_pairs(icp_align_warp_kernel<1, true>, ws, args, st);
-        case 2: return launch_pairs(icp_align_warp_kernel<2, true>, ws, args, st);
-        case 3: return launch_pairs(icp_align_warp_kernel<3, true>, ws, args, st);
-        default: return launch_pairs(icp_align_warp_kernel<4, true>, ws, args, st);
-      }
-    }
-    switch (SC) {
-      case 2: return launch_pairs(icp_align_warp_kernel<2, false>, ws, args, st);
-      case 4: return launch_pairs(icp_align_warp_kernel<4, false>, ws, args, st);
-      case 6: return launch_pairs(icp_align_warp_kernel<6, false>, ws, args, st);
-      case 8: return launch_pairs(icp_align_warp_kernel<8, false>, ws, args, st);
-      default: return launch_pairs(icp_align_warp_kernel<12, false>, ws, args, st);
-    }
+    const bool dense = env_int("B200ICP_PRUNE", 1) == 0 || (opt->flags & B200ICP_FLAG_DENSE_SWEEP);
+    B200ICP_DISPATCH_WARP(icp_align_warp_kernel, dense)
   }
   B200ICP_DISPATCH(icp_align_kernel)
 }

@@ -102,7 +102,11 @@ def test_nn_near_ties_and_exact_ties(b200):
         assert np.array_equal(idx[0, :len(src)].cpu().numpy(), ref)
 
 
-def test_nn_shapes_ragged_and_limits(b200):
+@pytest.mark.parametrize("nn_variant", [{}, {"B200ICP_PRUNE": "0"}, {"B200ICP_NN_BLOCK": "1"},
+                                        {"B200ICP_NN_BLOCK": "1", "B200ICP_SEARCH_DIRECT": "1"}])
+def test_nn_shapes_ragged_and_limits(b200, monkeypatch, nn_variant):
+    for k, v in nn_variant.items():
+        monkeypatch.setenv(k, v)
     rng = np.random.default_rng(11)
     cases = [(1, 1), (1, 7), (5, 1), (31, 33), (32, 8), (33, 9), (129, 257), (385, 77),
              (513, 1025), (1024, 4096), (1000, 4095)]
