@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="pairs", choices=["pairs", "odometry", "allpairs", "scan2map"],
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "odometry", "allpairs", "scan2map", "nn"],
                     help="pairs = the headline configs[2] (default); the others are BASELINE.json "
                          "configs[1], [3] and [4], reported with the same JSON shape")
     ap.add_argument("--map-points", type=int, default=1 << 24, help="scan2map: total map points")
@@ -528,6 +528,51 @@ def run_allpairs(args):
     print(json.dumps(line), flush=True)
 
 
+def run_nn(args):
+    """The correspondence search alone (b200icp_nn_batch, icp.py:37-38): one search per pair on the
+    configs[2] tables; the NN-phase number of the metric ("NN pairs/sec")."""
+    import torch
+    import icp_slam_yolo_b200 as m
+    from oracle import icp_oracle as orc
+    world, rank, local, dev, barrier, max_over_ranks = _dist_setup()
+    P = args.pairs
+    src_np, tgt_np = orc.synth_room_batch(rank * P, P)
+    src, tgt = m.ScanTable(torch.from_numpy(src_np).to(dev)), m.ScanTable(torch.from_numpy(tgt_np).to(dev))
+    idx = torch.empty((P, N_POINTS), dtype=torch.int32, device=dev)
+    d2 = torch.empty((P, N_POINTS), dtype=torch.float64, device=dev)
+    fp32_peak = m.ffma_probe()
+
+    def step():
+        m.nn_search(src, tgt, out_idx=idx, out_dist2=d2)
+
+    ms = _timed(step, args.steps, args.warmup, barrier, max_over_ranks)
+    os.environ["B200ICP_PRUNE"] = "0"
+    dense_ms = _timed(step, args.steps, args.warmup, barrier, max_over_ranks)
+    os.environ.pop("B200ICP_PRUNE")
+    if rank != 0:
+        return
+    evals = float(P) * N_POINTS * N_POINTS
+    line = {
+        "metric": "NN pairs/sec (360 x 360 brute-force-equivalent searches)", "value": world * evals / (ms * 1e-3),
+        "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 search + f64 re-decision", "data": "synthetic",
+        "config": {"workload": "configs[2] tables, ONE search per pair (%d pairs per GPU x 360 x 360)" % P,
+                   "l2": "inputs (377 MB) exceed L2; outputs idx + d2 = %.0f MB per step" % (P * N_POINTS * 12 / 1e6)},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "fp32", "kernel": "nn_warp_kernel<2,prune>", "achieved": evals * 5 / (ms * 1e-3) / 1e12,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": evals * 5 / (ms * 1e-3) / 1e12 / fp32_peak,
+                     "traffic": None,
+                     "dense_sweep": {"kernel": "nn_warp_kernel<6,dense>", "kernel_ms": dense_ms,
+                                     "frac": evals * 5 / (dense_ms * 1e-3) / 1e12 / fp32_peak},
+                     "hbm": {"achieved": P * N_POINTS * (16 + 12) / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                             "peak": measured_hbm_peak()[0],
+                             "note": "a single search per pair moves 28 B per source point: this kernel, unlike "
+                                     "the fused loop, is closer to the HBM roof than to the FP32 one"}},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_scan2map(args):
     """configs[4]: 8,192-point scan against a 2^24-point map sharded contiguously across the
     ranks; 30 forced iterations; one all-gather of 32-byte records per iteration."""
@@ -601,6 +646,8 @@ def main():
         run_allpairs(args)
     elif args.workload == "scan2map":
         run_scan2map(args)
+    elif args.workload == "nn":
+        run_nn(args)
     else:
         run_b200(args)
     try:
