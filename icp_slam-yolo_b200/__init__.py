@@ -5,9 +5,10 @@ Drop-in for the registration path of DucVuUET04/ICP_SLAM-YOLO
 behind a C ABI (include/b200icp.h); PyTorch only carries device memory and streams.
 """
 from ._cabi import B200IcpError, lib, library_path          # noqa: F401
-from .icp import IcpOutput, icp, icp_full, nearest_neighbors, registration_p2p   # noqa: F401
+from .icp import (IcpOutput, best_fit_transform, icp, icp_full, nearest_neighbors,   # noqa: F401
+                  registration_p2p)
 from .registration import (AlignResult, ScanTable, align_pairs, alloc_outputs,   # noqa: F401
-                           ffma_probe, nn_search, polar_to_cartesian)
+                           best_fit, ffma_probe, nn_search, polar_to_cartesian)
 from .odometry import align_consecutive, chain_poses         # noqa: F401
 from .sharding import shard_range, triangle_pair, triangle_pair_count   # noqa: F401
 from .scan_to_map import MapShard, ScanToMap, ScanToMapResult, scan_to_map_icp   # noqa: F401
@@ -16,7 +17,7 @@ from . import scan_io                                          # noqa: F401
 
 __all__ = [
     "B200IcpError", "lib", "library_path", "IcpOutput", "icp", "icp_full", "nearest_neighbors",
-    "registration_p2p", "AlignResult", "ScanTable", "align_pairs", "alloc_outputs", "ffma_probe",
+    "registration_p2p", "best_fit_transform", "best_fit", "AlignResult", "ScanTable", "align_pairs", "alloc_outputs", "ffma_probe",
     "nn_search", "polar_to_cartesian", "align_consecutive", "chain_poses", "shard_range",
     "triangle_pair", "triangle_pair_count", "scan_io", "MapShard", "ScanToMap", "ScanToMapResult",
     "scan_to_map_icp", "crop_local_map", "remove_dynamic_points", "voxel_down_sample",

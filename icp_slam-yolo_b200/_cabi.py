@@ -67,6 +67,7 @@ SYMBOLS = {
     "b200icp_nn_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200icp_align_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.POINTER(Options),
                                       C.POINTER(Outputs), C.c_void_p]),
+    "b200icp_best_fit_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p]),
     "b200icp_polar_to_cartesian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200icp_ffma_probe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_void_p]),

@@ -1283,6 +1283,56 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
 }
 
 // ------------------------------------------------------------------------------------
+// kernel: best_fit_transform(A, B) for matched rows (icp.py:5-26), one warp per pair:
+// centroids, centred 2x2 cross-covariance (single pass relative to B's first point),
+// closed-form proper rotation, t = cB - R cA.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) best_fit_warp_kernel(const KernelArgs a) {
+  const int lane = threadIdx.x;
+  const int64_t p = blockIdx.x;
+  const b200icp_problem& pr = a.prob;
+  int64_t srow, trow;
+  resolve_rows(pr, p, srow, trow);
+  const int ns = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
+  const int nt = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
+  const int n = min(ns, nt);
+  double* pose = a.out.pose_total + p * 6;
+  if (n <= 0) {
+    if (lane == 0) { pose[0] = 1; pose[1] = 0; pose[2] = 0; pose[3] = 1; pose[4] = 0; pose[5] = 0; }
+    return;
+  }
+  const double2 o = load_point(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch);
+  double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = lane; i < n; i += 32) {
+    const double2 s = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
+    const double2 b = load_point(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch + i);
+    const double ax = s.x - o.x, ay = s.y - o.y, qx = b.x - o.x, qy = b.y - o.y;
+    r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
+    r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
+    r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) r[q] += __shfl_xor_sync(kFull, r[q], s);
+  }
+  if (lane == 0) {
+    const double inv = 1.0 / (double)n;
+    const double max_ = r[0] * inv, may_ = r[1] * inv, mbx = r[2] * inv, mby = r[3] * inv;
+    const double h00 = fma(-r[0], mbx, r[4]), h01 = fma(-r[0], mby, r[5]);
+    const double h10 = fma(-r[1], mbx, r[6]), h11 = fma(-r[1], mby, r[7]);
+    const double num = h01 - h10, den = h00 + h11;
+    const double h2 = fma(num, num, den * den);
+    double cs = 1.0, sn = 0.0;
+    if (h2 > 0.0) { const double rh = rsqrt(h2); cs = den * rh; sn = num * rh; }
+    const double cax = o.x + max_, cay = o.y + may_;
+    pose[0] = cs; pose[1] = -sn; pose[2] = sn; pose[3] = cs;
+    pose[4] = (o.x + mbx) - (cs * cax - sn * cay);          // icp.py:25
+    pose[5] = (o.y + mby) - (sn * cax + cs * cay);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // kernel: scan preparation (process.py:38-52), one CTA per scan, order-preserving
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) polar_to_cartesian_kernel(
@@ -1708,6 +1758,23 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
     B200ICP_DISPATCH_WARP(icp_align_warp_kernel, dense)
   }
   B200ICP_DISPATCH(icp_align_kernel)
+}
+
+int b200icp_best_fit_batch(const b200icp_problem* prob, int64_t n_pairs, double* pose_out, void* stream) {
+  int rc = check_problem(prob, n_pairs);
+  if (rc == B200ICP_ERR_UNSUPPORTED_SHAPE) rc = B200ICP_OK;      // no shared-memory tile: any pitch
+  if (rc != B200ICP_OK) return rc;
+  if (!pose_out) { set_error("pose_out is NULL"); return B200ICP_ERR_INVALID_ARGUMENT; }
+  if (n_pairs == 0) return B200ICP_OK;
+  KernelArgs args;
+  memset(&args, 0, sizeof(args));
+  args.prob = *prob;
+  args.out.pose_total = pose_out;
+  args.n_pairs = n_pairs;
+  best_fit_warp_kernel<<<(unsigned)n_pairs, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "best_fit_warp_kernel");
+  return B200ICP_OK;
 }
 
 int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_t n_scans,

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from .registration import ScanTable, align_pairs, nn_search
+from .registration import ScanTable, align_pairs, best_fit, nn_search
 
 
 @dataclass
@@ -91,6 +91,17 @@ def icp(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_pose=No
     """
     o = icp_full(A, B, max_iterations, tolerance, init_pose=init_pose, max_corr_dist=max_corr_dist)
     return o.src, o.R_last, o.t_last
+
+
+def best_fit_transform(A, B) -> Tuple[np.ndarray, np.ndarray]:
+    """``best_fit_transform(A, B) -> (R, t)`` for matched rows (labels_segmentation/icp.py:5-26)."""
+    A = _as_points(A, "A")
+    B = _as_points(B, "B")
+    if len(A) != len(B):
+        raise ValueError("A and B must have the same number of rows")     # NumPy would fail to broadcast
+    pose = best_fit(ScanTable(torch.from_numpy(A[None]).cuda()), ScanTable(torch.from_numpy(B[None]).cuda()),
+                    n_pairs=1)[0].cpu().numpy()
+    return pose[:4].reshape(2, 2).copy(), pose[4:6].copy()
 
 
 def nearest_neighbors(src, tgt) -> Tuple[np.ndarray, np.ndarray]:

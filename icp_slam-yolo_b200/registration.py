@@ -252,6 +252,18 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     return out
 
 
+def best_fit(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None, stream=None) -> torch.Tensor:
+    """Rigid least-squares fit of matched rows, batched: ``best_fit_transform(A, B)``
+    (icp.py:5-26) for every pair; returns poses [B,6] (R row-major, t)."""
+    pr = _problem(src, tgt, "rowwise", None, None, 0)
+    b = min(src.rows, tgt.rows) if n_pairs is None else int(n_pairs)
+    pose = torch.empty((b, 6), dtype=torch.float64, device=src.points.device)
+    with torch.cuda.device(src.points.device):
+        rc = _cabi.lib().b200icp_best_fit_batch(C.byref(pr), b, _ptr(pose), _stream_ptr(stream))
+    _cabi.check(rc, "b200icp_best_fit_batch")
+    return pose
+
+
 def polar_to_cartesian(raw: torch.Tensor, raw_len: Optional[torch.Tensor] = None,
                        out_pitch: Optional[int] = None, stream=None) -> ScanTable:
     """Device scan preparation (process.py:38-52): raw [S, pitch, 3] float64 rows of

@@ -144,6 +144,15 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs,
                         void* stream);
 
 /*
+ * Least-squares rigid transform between MATCHED rows (row i of the source onto row i of the
+ * target, the first min(src_len, tgt_len) points of each pair).
+ * Replaces best_fit_transform(A, B) (labels_segmentation/icp.py:5-26).
+ *   pose_out [n_pairs][6] = R00 R01 R10 R11 tx ty.  Any pitch.  Degenerate H = 0 gives R = I.
+ */
+int b200icp_best_fit_batch(const b200icp_problem* prob, int64_t n_pairs, double* pose_out,
+                           void* stream);
+
+/*
  * Scan preparation on the device: quality / range / front-arc filter and
  * polar -> Cartesian with order-preserving compaction.
  * Replaces polar_to_cartesian_3d (duc/ICP_LIDAR/process.py:38-52).

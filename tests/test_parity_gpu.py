@@ -452,3 +452,18 @@ def test_dense_sweep_flag_gives_identical_bits(b200, cart_scans):
     assert torch.equal(a.pose_total, d.pose_total) and torch.equal(a.indices, d.indices)
     assert torch.equal(a.iterations, d.iterations) and torch.equal(a.error, d.error)
     assert int(a.evaluated_pairs.sum()) < int(d.evaluated_pairs.sum())      # something was culled
+
+
+def test_best_fit_transform_matches_reference_form(b200, cart_scans, golden):
+    """icp.py:5-26 on matched rows; the demo pair and real scans; batched ragged form."""
+    R, t = b200.best_fit_transform(golden["demo_A"], golden["demo_A_aligned"])
+    Ro, to = orc.best_fit_transform(golden["demo_A"], golden["demo_A_aligned"])
+    assert np.allclose(R, Ro, atol=1e-12) and np.allclose(t, to, atol=1e-12)
+    P = [cart_scans[k][:100] for k in (5, 40, 300)] + [cart_scans[7][:3]]
+    Q = [cart_scans[k + 1][:100] for k in (5, 40, 300)] + [cart_scans[8][:3]]
+    poses = b200.best_fit(b200.ScanTable.from_list(P), b200.ScanTable.from_list(Q)).cpu().numpy()
+    for k in range(len(P)):
+        Ro, to = orc.best_fit_transform(P[k], Q[k])
+        assert np.allclose(poses[k, :4].reshape(2, 2), Ro, atol=1e-11) and np.allclose(poses[k, 4:], to, atol=1e-7)
+    with pytest.raises(ValueError):
+        b200.best_fit_transform(P[0], Q[0][:50])
