@@ -14,6 +14,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
+from . import _cabi
 from .registration import ScanTable, align_pairs, best_fit, nn_search
 
 
@@ -63,6 +64,9 @@ def icp_full(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_po
     """One alignment with every output of the new call surface."""
     A = _as_points(A, "A")
     B = _as_points(B, "B")
+    lib = _cabi.lib()
+    if len(A) > lib.b200icp_max_src_pitch() or len(B) > lib.b200icp_max_tgt_pitch():
+        return _icp_full_large(A, B, max_iterations, tolerance, init_pose, max_corr_dist)
     src = ScanTable(torch.from_numpy(A[None]).cuda(), None)
     tgt = ScanTable(torch.from_numpy(B[None]).cuda(), None)
     res = align_pairs(src, tgt, n_pairs=1, max_iterations=max_iterations, tolerance=tolerance,
@@ -79,6 +83,22 @@ def icp_full(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_po
         indices=res.indices[0].cpu().numpy().astype(np.intp),
         src=res.src_final[0].cpu().numpy(),
     )
+
+
+def _icp_full_large(A, B, max_iterations, tolerance, init_pose, max_corr_dist) -> IcpOutput:
+    """Point sets beyond the fused per-pair kernel (> 1,024 source or > 4,096 target points, e.g. a
+    scan against the 11 k-point local map of the reference's SLAM loop): the sharded-map path with
+    a single shard -- same loop, same exactness, any size."""
+    from .scan_to_map import MapShard, ScanToMap
+    s2m = ScanToMap(MapShard(torch.from_numpy(B).cuda()), len(A), want_indices=True, local_only=True)
+    ip = None
+    if init_pose is not None:
+        ip = _pose6(init_pose)[0].cpu().numpy()
+    r = s2m.run(torch.from_numpy(A).cuda(), max_iterations=max_iterations, tolerance=tolerance,
+                init_pose=ip, max_corr_dist=max_corr_dist)
+    return IcpOutput(R=r.R, t=r.t, error=r.error, iterations=r.iterations, R_last=r.R_last, t_last=r.t_last,
+                     rmse=r.rmse, fitness=r.inliers / float(len(A)),
+                     indices=r.indices.cpu().numpy().astype(np.intp), src=r.src.cpu().numpy())
 
 
 def icp(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_pose=None,

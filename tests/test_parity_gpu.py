@@ -467,3 +467,21 @@ def test_best_fit_transform_matches_reference_form(b200, cart_scans, golden):
         assert np.allclose(poses[k, :4].reshape(2, 2), Ro, atol=1e-11) and np.allclose(poses[k, 4:], to, atol=1e-7)
     with pytest.raises(ValueError):
         b200.best_fit_transform(P[0], Q[0][:50])
+
+
+def test_icp_drop_in_handles_large_sets(b200):
+    """A scan against a local map larger than the fused kernel's tile (the reference's saved map has
+    11,283 points, global_map_offline.pcd): icp() routes through the sharded-map path."""
+    mp = orc.synth_map(11283, dtype=np.float64)
+    sc = orc.synth_scan_for_map(1500, dtype=np.float64)
+    o = orc.icp_extended(sc, mp, 30, 1e-5)
+    r = b200.icp_full(sc, mp, 30, 1e-5)
+    assert r.iterations == o.iterations and np.array_equal(r.indices, o.indices[-1])
+    assert np.allclose(r.R, o.R_tot, atol=1e-9) and np.allclose(r.t, o.t_tot, atol=1e-6)
+    assert np.allclose(r.src, o.src, atol=1e-6) and abs(r.error - o.error) < 1e-9 * max(1.0, o.error)
+    src, R, t = b200.icp(sc, mp, 30, 1e-5)
+    assert np.allclose(R, o.R_last, atol=1e-9) and np.allclose(t, o.t_last, atol=1e-6)
+    g = b200.icp_full(sc, mp, 30, 1e-5, init_pose=(np.eye(2), np.array([3.0, -2.0])), max_corr_dist=60.0)
+    og = orc.icp_extended(sc, mp, 30, 1e-5, init_pose=(np.eye(2), np.array([3.0, -2.0])), max_corr_dist=60.0)
+    assert g.iterations == og.iterations and abs(g.rmse - og.rmse) < 1e-9 * max(1.0, og.rmse)
+    assert abs(g.fitness - og.fitness) < 1e-12
