@@ -485,3 +485,44 @@ def test_icp_drop_in_handles_large_sets(b200):
     og = orc.icp_extended(sc, mp, 30, 1e-5, init_pose=(np.eye(2), np.array([3.0, -2.0])), max_corr_dist=60.0)
     assert g.iterations == og.iterations and abs(g.rmse - og.rmse) < 1e-9 * max(1.0, og.rmse)
     assert abs(g.fitness - og.fitness) < 1e-12
+
+
+def test_nn_randomised_stress_exact_indices(b200):
+    """2,400 random ragged problems: clustered, lattice (exact ties -> lowest index), collinear,
+    duplicated, huge offsets (1e6) and tiny scales (1e-3): the pruned FP32 sweep + float64
+    re-decision must equal the float64 brute-force argmin everywhere."""
+    rng = np.random.default_rng(2024)
+    A, B = [], []
+    for q in range(2400):
+        n, m = int(rng.integers(1, 200)), int(rng.integers(1, 260))
+        kind = q % 6
+        scale = [1.0, 1e3, 1e-3, 50.0, 1e4, 7.0][q % 6 if q % 12 < 6 else (q + 1) % 6]
+        off = rng.uniform(-1, 1, 2) * (1e6 if q % 7 == 0 else 1e3)
+        if kind == 0:                       # gaussian blobs
+            a, b = rng.normal(0, 1, (n, 2)), rng.normal(0, 1, (m, 2))
+        elif kind == 1:                     # integer lattice: many exact ties
+            a, b = rng.integers(-6, 7, (n, 2)).astype(float), rng.integers(-6, 7, (m, 2)).astype(float)
+        elif kind == 2:                     # collinear
+            a = np.stack([np.sort(rng.uniform(-5, 5, n)), np.zeros(n)], 1)
+            b = np.stack([np.sort(rng.uniform(-5, 5, m)), rng.normal(0, 1e-9, m)], 1)
+        elif kind == 3:                     # duplicates of a few sites
+            sites = rng.normal(0, 3, (5, 2))
+            a, b = sites[rng.integers(0, 5, n)] + rng.normal(0, 0.01, (n, 2)), sites[rng.integers(0, 5, m)]
+        elif kind == 4:                     # ordered arcs (prunable)
+            ta, tb = np.sort(rng.uniform(0, 6.28, n)), np.sort(rng.uniform(0, 6.28, m))
+            a = np.stack([np.cos(ta), np.sin(ta)], 1) * 3 + rng.normal(0, 0.01, (n, 2))
+            b = np.stack([np.cos(tb), np.sin(tb)], 1) * 3
+        else:                               # far apart clusters
+            a, b = rng.normal(0, 0.3, (n, 2)) + 40.0, rng.normal(0, 0.3, (m, 2))
+        A.append(a * scale + off); B.append(b * scale + off)
+    for dt in (np.float64, np.float32):
+        s, t = b200.ScanTable.from_list(A, dtype=dt), b200.ScanTable.from_list(B, dtype=dt)
+        idx, d2 = b200.nn_search(s, t)
+        idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
+        hs, ht = s.points.cpu().numpy().astype(np.float64), t.points.cpu().numpy().astype(np.float64)
+        for q in range(len(A)):
+            n, m = len(A[q]), len(B[q])
+            dd = ((hs[q, :n, None, :] - ht[q, None, :m, :]) ** 2).sum(axis=2)
+            ref = dd.argmin(axis=1)
+            assert np.array_equal(idx[q, :n], ref), f"problem {q} ({dt.__name__}, kind {q % 6})"
+            assert np.array_equal(d2[q, :n], dd[np.arange(n), ref])
