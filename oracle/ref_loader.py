@@ -57,3 +57,37 @@ def load_reference_icp():
                 sys.modules[k] = v
     _cached = mod
     return mod
+
+
+_PROCESS_PATH = os.path.join(REFERENCE_ROOT, "duc", "ICP_LIDAR", "process.py")
+_cached_process = None
+
+
+def load_reference_process():
+    """The UNMODIFIED ``duc/ICP_LIDAR/process.py`` (build container only): ``bresenham_line``,
+    ``update_occupancy_map``, ``filter_new_points_by_occupancy``, ``polar_to_cartesian_3d``.
+    It imports ``open3d`` (process.py:1, and through gicp_lidar.py), which is not installed; an
+    empty stub module stands in for the duration of the import (none of the functions named
+    above touches it).  ``cv2``, ``Config`` and ``gicp_lidar`` are the real ones."""
+    global _cached_process
+    if _cached_process is not None:
+        return _cached_process
+    if not os.path.isfile(_PROCESS_PATH):
+        raise FileNotFoundError(_PROCESS_PATH)
+    ref_dir = os.path.dirname(_PROCESS_PATH)
+    saved = {k: sys.modules.get(k) for k in ("open3d", "gicp_lidar", "Config")}
+    sys.modules["open3d"] = types.ModuleType("open3d")
+    sys.path.insert(0, ref_dir)
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_process", _PROCESS_PATH)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(ref_dir)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cached_process = mod
+    return mod
