@@ -58,6 +58,15 @@ class S2MShard(C.Structure):
     ]
 
 
+class OccGrid(C.Structure):
+    _fields_ = [
+        ("probs", C.c_void_p), ("image", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32),
+        ("center_x", C.c_double), ("center_y", C.c_double), ("resolution", C.c_double),
+        ("area", C.c_int32), ("p_occ_inc", C.c_float), ("p_free_dec", C.c_float),
+        ("threshold_up", C.c_float),
+    ]
+
+
 # symbol -> (restype, argtypes); must list EVERY function include/b200icp.h declares
 SYMBOLS = {
     "b200icp_version": (C.c_int, []),
@@ -77,6 +86,11 @@ SYMBOLS = {
     "b200icp_voxel_workspace_bytes": (C.c_int64, [C.c_int64]),
     "b200icp_voxel_downsample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200icp_occ_update": (C.c_int, [C.POINTER(OccGrid), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200icp_occ_filter_points": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                            C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                            C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200icp_s2m_chunk": (C.c_int, []),
     "b200icp_s2m_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p]),

@@ -282,6 +282,58 @@ int b200icp_voxel_downsample(const void* points, int32_t dtype, int64_t n, doubl
                              int64_t workspace_bytes, void* stream);
 
 /*
+ * Occupancy-grid ray casting (the mapping step that follows registration in the SLAM loop).
+ * Replaces update_occupancy_map (duc/ICP_LIDAR/process.py:114-177; same body at
+ * duc/ICP_LIDAR/slam_offline.py:174-236; called at mainn.py:340,749 and slam_offline.py:341,419)
+ * including bresenham_line (process.py:86-112).  Bit-identical to the reference.
+ *   probs : the reference keeps the probabilities in the function attribute
+ *           update_occupancy_map.occupancy_probs (process.py:122-125), created as 0.5 everywhere;
+ *           here the caller owns them.   image : the `occupancy_map` argument (h, w, 3) uint8; its
+ *           window around the robot is re-rendered as grey levels after every frame
+ *           (process.py:172-176).  NULL skips the rendering.
+ * Per frame: window of +-area cells around the robot cell; for every point, in order, a ray
+ * from the robot cell to the point's cell: cells before the end are multiplied by p_free_dec
+ * until one is >= threshold_up (that ends the ray and the end cell is NOT raised), the end cell is
+ * raised by p_occ_inc and clamped to 1.  Frames with no points change nothing.  Points with
+ * non-finite coordinates are skipped (the reference raises on them).
+ * float32 parameters: NumPy 2 evaluates `np.float32 * 0.9` with float32(0.9) (the caller passes
+ * the rounded constants).
+ */
+typedef struct b200icp_occ_grid {
+  float* probs;            /* [n_maps][h][w] float32, updated in place                       */
+  uint8_t* image;          /* [n_maps][h][w][3] uint8 or NULL                                 */
+  int32_t h, w;            /* cells; <= 32768 each                                            */
+  double center_x, center_y; /* map_center_px (slam_offline.py:320)                           */
+  double resolution;       /* mm per cell (Config.py:7)                                       */
+  int32_t area;            /* half window in cells (process.py:115: 140); <= 10000            */
+  float p_occ_inc;         /* process.py:115: float32(0.2)                                    */
+  float p_free_dec;        /* process.py:115: float32(0.9)                                    */
+  float threshold_up;      /* process.py:158: float32(0.65)                                   */
+} b200icp_occ_grid;
+
+/*
+ * n_maps independent grids (one CTA each), n_frames frames applied to each in order:
+ *   points   [n_maps][n_frames][pitch][2] map-frame coordinates (dtype f32/f64)
+ *   len      [n_maps][n_frames] valid points per frame (NULL = pitch)
+ *   robot_xy [n_maps][n_frames][2] float64 robot position (global_pose[:2, 3])
+ */
+int b200icp_occ_update(const b200icp_occ_grid* grid, int32_t n_maps, const void* points, int32_t dtype,
+                       const int32_t* len, const double* robot_xy, int32_t n_frames, int32_t pitch,
+                       void* stream);
+
+/*
+ * Point filter on cell probabilities.  Replaces filter_new_points_by_occupancy
+ * (duc/ICP_LIDAR/process.py:203-226) and prune_global_map (process.py:228-249): point i is dropped
+ * iff its cell lies inside the grid and probs[py, px] < free_threshold.
+ *   points [n][cols] rows (x, y, ...), cols >= 2;  kept_index [n] int64: the kept row numbers in
+ *   order (first *count_out entries);  scratch: int64[ceil(n/1024) + 1].
+ */
+int b200icp_occ_filter_points(const void* points, int32_t dtype, int32_t cols, int64_t n, const float* probs,
+                              int32_t h, int32_t w, double center_x, double center_y, double resolution,
+                              float free_threshold, int64_t* kept_index, int64_t* count_out,
+                              int64_t* scratch, void* stream);
+
+/*
  * FP32 FFMA throughput probe used as the roofline denominator of the NN phase
  * (MEASURED_PEAKS.json carries no FP32 figure).  Launches one kernel doing
  * `flop_out[0]` floating point operations (written to a HOST int64); the caller

@@ -57,7 +57,7 @@ void occ_update(float* occ, uint8_t* image, int h, int w, const double* pts, int
           float* c = &occ[(y1 + y) * w + (x1 + x)];
           if (*c >= thr_up) { stopped = 1; break; }
           const float v = *c * p_free_dec;
-          *c = 0.0f > v ? 0.0f : v;            /* max(0.0, v) */
+          *c = v > 0.0f ? v : 0.0f;            /* max(0.0, v): Python returns 0.0 unless v > 0.0 */
         }
         e2 -= 2 * dy;
         if (e2 < 0) { y += sy; e2 += 2 * dx; }
@@ -70,7 +70,7 @@ void occ_update(float* occ, uint8_t* image, int h, int w, const double* pts, int
           float* c = &occ[(y1 + y) * w + (x1 + x)];
           if (*c >= thr_up) { stopped = 1; break; }
           const float v = *c * p_free_dec;
-          *c = 0.0f > v ? 0.0f : v;
+          *c = v > 0.0f ? v : 0.0f;
         }
         e2 -= 2 * dx;
         if (e2 < 0) { x += sx; e2 += 2 * dy; }

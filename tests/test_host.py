@@ -133,3 +133,40 @@ def test_scan_io(pkg, raw_scans, tmp_path):
     assert raw.shape == (4, max(len(r) for r in raw_scans[:4]), 3) and lens.tolist() == [len(r) for r in raw_scans[:4]]
     fx = pkg.scan_io.unpack_fixture(os.path.join(ROOT, "tests", "golden", "scan_data_1_packed.npz"))
     assert len(fx) == 1831 and np.array_equal(fx[7], raw_scans[7])
+
+
+def test_map_io_pcd_and_png_round_trip(tmp_path):
+    """The reference's map outputs (slam_offline.py:445-453): binary x y z float32 PCD as Open3D
+    writes it and an 8-bit RGB PNG as cv2.imwrite does."""
+    import icp_slam_yolo_b200 as pkg
+    rng = np.random.Generator(np.random.PCG64(3))
+    pts = rng.normal(0, 3000, size=(257, 2))
+    p = str(tmp_path / "map.pcd")
+    pkg.map_io.write_pcd(p, pts)
+    back = pkg.map_io.read_pcd(p)
+    assert back.shape == (257, 3) and np.array_equal(back[:, :2], pts.astype(np.float32)) and not back[:, 2].any()
+    blob = open(p, "rb").read()
+    assert blob.startswith(b"# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\n")
+    assert b"\nWIDTH 257\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 257\nDATA binary\n" in blob
+    ref_pcd = "/root/reference/global_map_offline.pcd"
+    if os.path.exists(ref_pcd):                      # build container: re-writing the bundled map is the identity
+        q = str(tmp_path / "again.pcd")
+        pkg.map_io.write_pcd(q, pkg.map_io.read_pcd(ref_pcd))
+        assert open(q, "rb").read() == open(ref_pcd, "rb").read()
+
+    img = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    f = str(tmp_path / "occ.png")
+    pkg.map_io.write_png(f, img)
+    assert np.array_equal(pkg.map_io.read_png(f), img)
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:
+        assert np.array_equal(cv2.imread(f, cv2.IMREAD_UNCHANGED), img)          # OpenCV decodes our file
+        g = str(tmp_path / "cv.png")
+        cv2.imwrite(g, img)
+        assert np.array_equal(pkg.map_io.read_png(g), img)                         # and we decode OpenCV's
+    ref_png = "/root/reference/realtime_occupancy_map.png"
+    if cv2 is not None and os.path.exists(ref_png):
+        assert np.array_equal(pkg.map_io.read_png(ref_png), cv2.imread(ref_png, cv2.IMREAD_UNCHANGED))
