@@ -71,6 +71,7 @@ struct KernelArgs {
   int32_t mcap;         // tgt_pitch rounded up to kGroup
   int32_t ncap;         // warp kernel: src_pitch rounded up to 32 * SC
   int32_t use_gate;
+  int32_t reuse;        // fused warp kernel: skip the sweep of a pass while its sources provably keep their group
 };
 
 // ------------------------------------------------------------------------------------
@@ -656,14 +657,18 @@ struct WarpTile {
   float* gcx;           // [mcap/8] bounding circle of each group of 8 targets (pruned sweep)
   float* gcy;
   float* grad;
+  unsigned short* grp;  // [ncap] group of every source's nearest neighbour at its last full sweep
   double ox, oy;
   float tmax;
   int m, mcap, ngroups;
 };
 
+constexpr int kCtxBytes = 400;        // WarpCtx, padded to 16 bytes
+constexpr int kMaxPasses = 32;        // kMaxSrcPitch / 32
 __host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap) {
-  return (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + 160 /* WarpCtx */ +
-         (size_t)(mcap / kGroup) * 3 * sizeof(float);
+  const size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
+                   (size_t)(mcap / kGroup) * 3 * sizeof(float) + (size_t)ncap * sizeof(unsigned short);
+  return (b + 15) & ~(size_t)15;
 }
 
 __device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
@@ -855,7 +860,7 @@ __device__ __forceinline__ float box_dist2(float px, float py, float x0, float x
 template <int S>
 __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
                                                       const float (&sy)[S], const bool (&valid)[S],
-                                                      Candidates<S>& c) {
+                                                      Candidates<S>& c, float reach_scale, float& reach_out) {
   int evaluated = 0;            // groups swept in this pass (diagnostics)
   float a[S], b[S], ss[S];
   float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
@@ -904,7 +909,10 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
   // slot-level margin >= every lane's is_ambiguous margin (monotone in cs); + the FP32 rounding
   // of |s|^2 itself (<= 4u * csk^2).  +inf if stage A hit nothing.
   const float margin = expanded_margin(csk, t.tmax);
-  const float reach = sqrtf(fmaxf(ub2, 0.f) + 3.f * margin + csk * csk * 4.8e-7f) * 1.000004f;
+  // reach_scale > 1 (sweep reuse): groups a little beyond the strict need are swept too, so that
+  // every source learns a lower bound (reach) of its distance to all the groups NOT swept
+  const float reach = sqrtf(fmaxf(ub2, 0.f) + 3.f * margin + csk * csk * 4.8e-7f) * 1.000004f * reach_scale;
+  reach_out = reach;
   // ---- stage B: the remaining groups that can still matter
   for (int w = 0; w < words; ++w) {
     float d2, rr;
@@ -969,32 +977,69 @@ struct WarpCtx {
   double err, mean_d2, prev_error;
   double inv_n;
   int iters, inl;
+  // sweep reuse: cum_move bounds how far any source point has moved since the start (sum of the
+  // per-iteration maximum displacements); pass q may skip its sweep while cum_move <= tpass[q]
+  double cum_move;
+  double tpass[kMaxPasses];
 };
+static_assert(sizeof(WarpCtx) <= kCtxBytes, "WarpCtx outgrew its shared-memory slot");
 
 // One pass of the correspondence search: the exact nearest target index j[k] for the SC source
 // points (base + k*32 + lane) of every lane, read from the float64 source state in shared memory.
 // Candidate sweep (FP32, pruned or dense) -> FP32 in-group argmin -> guards -> rare
 // warp-cooperative float64 rescans.  Returns the pair evaluations the sweep executed.
+// Sweep reuse (fused loop): `reuse` skips the sweep and re-decides inside the group stored at the
+// last full sweep; lb[k] (full sweeps only) is a lower bound of the distance from source k to
+// every target OUTSIDE its best group -- the runner-up group of the sweep minus the FP32 error
+// band, and `reach` for the groups the pruned sweep did not visit.  While a point has moved less
+// than (lb - d_nn) / 2 since then, no outside target can have become its nearest neighbour.
 template <int SC, bool PRUNE>
 __device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int base, int n, int m,
-                                                      int lane, int (&j)[SC]) {
+                                                      int lane, int (&j)[SC], bool reuse, bool track,
+                                                      float (&lb)[SC]) {
   long long evals = 0;
   float fx[SC], fy[SC];
 #pragma unroll
   for (int k = 0; k < SC; ++k) {
     const double2 s = t.src[base + k * 32 + lane];
     fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
+    lb[k] = -1.f;
   }
   Candidates<SC> c;
-  if (PRUNE) {
+  if (reuse) {
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      c.group[k] = t.grp[base + k * 32 + lane];
+      c.best[k] = 0.f; c.second[k] = CUDART_INF_F;        // cross-group guard: settled by the movement bound
+    }
+  } else if (PRUNE) {
     bool vld[SC];
 #pragma unroll
     for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
-    const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c);
+    float reach;
+    const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c, track ? 2.0f : 1.0f, reach);
     evals += (long long)groups * kGroup * min(32 * SC, n - base);
+    if (track) {
+#pragma unroll
+      for (int k = 0; k < SC; ++k) lb[k] = reach * 0.999996f;
+    }
   } else {
     warp_candidates<SC>(t, fx, fy, c);
     evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
+    if (track) {
+#pragma unroll
+      for (int k = 0; k < SC; ++k) lb[k] = CUDART_INF_F;
+    }
+  }
+  if (track && !reuse) {
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      // runner-up group: d^2 >= second + |s|^2 - (FP32 error of the expanded form and of |s|^2)
+      const float cs = fmaxf(fabsf(fx[k]), fabsf(fy[k]));
+      const float ss = fmaf(fx[k], fx[k], fy[k] * fy[k]);
+      const float lo2 = (c.second[k] + ss) - (2.f * expanded_margin(cs, t.tmax) + cs * cs * 4.8e-7f);
+      lb[k] = fminf(lb[k], sqrtf(fmaxf(lo2, 0.f)) * 0.999996f);
+    }
   }
   bool amb[SC];
   bool any_amb = false;
@@ -1004,7 +1049,7 @@ __device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int bas
     const int slot = in_group_argmin(t, c.group[k], fx[k], fy[k], tie_in);
     j[k] = c.group[k] * kGroup + slot;
     amb[k] = (base + k * 32 + lane < n) &&
-             (tie_in || is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax));
+             (tie_in || (!reuse && is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax)));
     any_amb |= amb[k];
   }
   if (__any_sync(kFull, any_amb)) {      // rare: warp-cooperative float64 scan
@@ -1035,6 +1080,13 @@ __device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int bas
       j[k] = jk;
     }
   }
+  if (track && !reuse) {
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      if ((j[k] >> 3) != c.group[k]) lb[k] = -1.f;       // float64 rescan picked another group: no bound
+      t.grp[base + k * 32 + lane] = (unsigned short)(j[k] >> 3);
+    }
+  }
   return evals;
 }
 
@@ -1045,9 +1097,10 @@ __device__ __forceinline__ void carve_warp_tile(unsigned char* smem, const Kerne
   t.tile = reinterpret_cast<float*>(smem);
   t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);  // 12*mcap bytes, mcap % 8 == 0
   ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
-  t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + 160);
+  t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + kCtxBytes);
   t.gcy = t.gcx + a.mcap / kGroup;
   t.grad = t.gcy + a.mcap / kGroup;
+  t.grp = reinterpret_cast<unsigned short*>(t.grad + a.mcap / kGroup);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1084,7 +1137,8 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) nn_warp_kernel(co
   __syncwarp();
   for (int base = 0; base < n; base += 32 * SC) {
     int j[SC];
-    warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j);
+    float lb_unused[SC];
+    warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j, false, false, lb_unused);
 #pragma unroll
     for (int k = 0; k < SC; ++k) {
       const int i = base + k * 32 + lane;
@@ -1136,8 +1190,11 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
     ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->prev_error = 0.0;   // icp.py:33
     ctx->inv_n = n > 0 ? 1.0 / (double)n : 0.0;
     ctx->iters = 0; ctx->inl = 0;
+    ctx->cum_move = 0.0;
   }
+  ctx->tpass[lane] = -CUDART_INF;                 // kMaxPasses == 32: no pass may skip its first sweep
   __syncwarp();
+  const bool track = a.reuse != 0;
   int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
   long long evals = 0;          // pair evaluations executed by the sweep (padded targets included)
 
@@ -1163,7 +1220,11 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
       for (int base = 0; base < n; base += 32 * SC) {
         // ---- correspondence search for the SC sources of every lane (icp.py:37-38)
         int j[SC];
-        evals += warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j);
+        float lb[SC];
+        const int pass = base / (32 * SC);
+        const bool reuse = track && ctx->cum_move <= ctx->tpass[pass];
+        evals += warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j, reuse, track, lb);
+        float budget = CUDART_INF_F;
         // ---- gather (icp.py:39): all SC loads in flight before the first use
         double2 bm[SC];
 #pragma unroll
@@ -1181,6 +1242,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
             const double2 b = bm[k];
             const double d2 = dist2_f64(s.x, s.y, b);
             const double dist = sqrt_f64_fast(d2);
+            budget = fminf(budget, 0.5f * (lb[k] - __double2float_ru(dist) * 1.000001f));
             if (!use_gate || dist < gate) {
               const double ax = s.x - t.ox, ay = s.y - t.oy;
               const double qx = b.x - t.ox, qy = b.y - t.oy;
@@ -1192,6 +1254,10 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
             if (idx_out) idx_out[i] = j[k];
             if (hist) hist[i] = j[k];
           }
+        }
+        if (track && !reuse) {       // how far the points of this pass may move before it must sweep again
+          budget = warp_min_f32(budget);
+          if (lane == 0) ctx->tpass[pass] = budget > 0.f ? ctx->cum_move + 0.999 * (double)budget : -CUDART_INF;
         }
       }
 #pragma unroll
@@ -1222,13 +1288,20 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
       const double cax = t.ox + max_, cay = t.oy + may_;
       const double tx = (t.ox + mbx) - (cs * cax - sn * cay);  // icp.py:25
       const double ty = (t.oy + mby) - (sn * cax + cs * cay);
+      double mv2 = 0.0;
       for (int i = lane; i < n; i += 32) {                     // apply (icp.py:45)
         const double2 s = t.src[i];
-        t.src[i] = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
+        const double2 v = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
+        t.src[i] = v;
+        const double mx = v.x - s.x, my = v.y - s.y;
+        mv2 = fmax(mv2, fma(mx, mx, my * my));
       }
+      float mv = 0.f;
+      if (track) mv = warp_max_f32(__fsqrt_ru(__double2float_ru(mv2)));   // largest displacement, rounded up
       const bool converged = fabs(ctx->prev_error - mean_error) < op.tolerance;   // icp.py:49-50
       __syncwarp();
       if (lane == 0) {            // compose the cumulative pose, record the increment
+        ctx->cum_move += (double)mv * 1.000001;
         const double R00 = ctx->R[0], R01 = ctx->R[1], R10 = ctx->R[2], R11 = ctx->R[3];
         const double T0 = ctx->T[0], T1 = ctx->T[1];
         ctx->R[0] = cs * R00 - sn * R10; ctx->R[1] = cs * R01 - sn * R11;
@@ -1752,6 +1825,7 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   args.n_pairs = n_pairs;
   args.mcap = ls.mcap;
   args.use_gate = (opt->max_corr_dist > 0.0 && std::isfinite(opt->max_corr_dist)) ? 1 : 0;
+  args.reuse = (env_int("B200ICP_REUSE", 1) != 0 && !(opt->flags & B200ICP_FLAG_NO_SWEEP_REUSE)) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (env_int("B200ICP_ALIGN_BLOCK", 0) == 0) {
     const bool dense = env_int("B200ICP_PRUNE", 1) == 0 || (opt->flags & B200ICP_FLAG_DENSE_SWEEP);

@@ -90,6 +90,13 @@ typedef struct b200icp_problem {
                                        sweep is ~2x faster on spatially ordered scans (LiDAR beams)
                                        and ~15 % slower on unordered point sets.             */
 
+#define B200ICP_FLAG_NO_SWEEP_REUSE 2  /* sweep every pass in every iteration.  By default a pass of
+                                          64 source points skips its candidate sweep while none of
+                                          them can have left the group of 8 targets that held its
+                                          nearest neighbour at the last sweep (a bound on the motion
+                                          since then against the gap to the nearest outside target);
+                                          the correspondences are identical either way.            */
+
 typedef struct b200icp_options {
   int32_t max_iterations;   /* icp.py:28,35; reference default 20                   */
   int32_t flags;            /* B200ICP_FLAG_*                                        */

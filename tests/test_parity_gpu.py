@@ -339,6 +339,8 @@ _VARIANTS = {
     "warp-pruned-S1": {"B200ICP_PRUNE_S": "1"},
     "warp-pruned-S4": {"B200ICP_PRUNE_S": "4"},
     "warp-dense": {"B200ICP_PRUNE": "0"},
+    "warp-pruned-no-reuse": {"B200ICP_REUSE": "0"},
+    "warp-dense-no-reuse": {"B200ICP_PRUNE": "0", "B200ICP_REUSE": "0"},
     "block-expanded": {"B200ICP_ALIGN_BLOCK": "1"},
     "block-direct": {"B200ICP_ALIGN_BLOCK": "1", "B200ICP_SEARCH_DIRECT": "1"},
 }
@@ -452,6 +454,27 @@ def test_dense_sweep_flag_gives_identical_bits(b200, cart_scans):
     assert torch.equal(a.pose_total, d.pose_total) and torch.equal(a.indices, d.indices)
     assert torch.equal(a.iterations, d.iterations) and torch.equal(a.error, d.error)
     assert int(a.evaluated_pairs.sum()) < int(d.evaluated_pairs.sum())      # something was culled
+
+
+def test_sweep_reuse_gives_identical_bits_and_skips_sweeps(b200, cart_scans):
+    """Passes skip their candidate sweep while the points provably keep their group: same
+    correspondences at every iteration, same poses bit for bit, far fewer evaluated pairs --
+    on real scans (early exit) and on synthetic rooms with 30 forced iterations."""
+    table = b200.ScanTable.from_list(cart_scans[900:1028])
+    kw = dict(max_iterations=30, tolerance=1e-5, want_indices=True, want_stats=True, want_history=True)
+    a = b200.align_consecutive(table, **kw)
+    d = b200.align_consecutive(table, sweep_reuse=False, **kw)
+    assert torch.equal(a.index_history, d.index_history) and torch.equal(a.pose_total, d.pose_total)
+    assert torch.equal(a.iterations, d.iterations) and torch.equal(a.error, d.error)
+    assert int(a.evaluated_pairs.sum()) < int(d.evaluated_pairs.sum())
+    src, tgt = orc.synth_room_batch(4000, 64)
+    s, t = b200.ScanTable(torch.from_numpy(src).cuda()), b200.ScanTable(torch.from_numpy(tgt).cuda())
+    kw = dict(max_iterations=30, tolerance=-1.0, want_stats=True, want_history=True)
+    a = b200.align_pairs(s, t, **kw)
+    d = b200.align_pairs(s, t, sweep_reuse=False, **kw)
+    assert torch.equal(a.index_history, d.index_history) and torch.equal(a.pose_total, d.pose_total)
+    assert torch.equal(a.error, d.error)
+    assert int(a.evaluated_pairs.sum()) * 2 < int(d.evaluated_pairs.sum())       # most sweeps are skipped
 
 
 def test_best_fit_transform_matches_reference_form(b200, cart_scans, golden):
