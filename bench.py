@@ -277,11 +277,11 @@ def run_b200(args):
     # brute-force FP32 roofline number; identical results required
     dense_out = m.alloc_outputs(P, N_POINTS, dev)
     for _ in range(2):
-        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, dense_sweep=True, out=dense_out)
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, dense_sweep=True, sweep_reuse=False, out=dense_out)
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d0.record()
     for _ in range(3):
-        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, dense_sweep=True, out=dense_out)
+        m.align_pairs(src, tgt, max_iterations=ITERS, tolerance=-1.0, dense_sweep=True, sweep_reuse=False, out=dense_out)
     d1.record()
     torch.cuda.synchronize()
     dense_ms = d0.elapsed_time(d1) / 3
@@ -338,19 +338,22 @@ def run_b200(args):
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                      "peak_source": "b200icp_ffma_probe measured live (dependent-FFMA chains, all SMs)",
                      "algorithmic_flop_per_launch": flops, "kernel_ms": kernel_ms,
-                     "traffic": 391111168 if P == 65536 else None,
+                     "traffic": 390157824 if P == 65536 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                       "capture profiles/r1g_align_pruned_final_ncu.txt (algorithmic: 380.6 MB)",
+                                       "capture profiles/r1i_align_reuse_ncu.txt (algorithmic: 380.6 MB)",
                      "executed_pair_eval_fraction": executed / (P * PAIR_EVALS_PER_ALIGNMENT),
                      "executed_tflops": executed * FLOP_PER_PAIR_EVAL / (kernel_ms * 1e-3) / 1e12,
-                     "dense_sweep": {"kernel": "icp_align_warp_kernel<6,dense> (B200ICP_FLAG_DENSE_SWEEP: every pair-eval "
-                                               "executed; bit-identical poses)", "kernel_ms": dense_ms,
+                     "dense_sweep": {"kernel": "icp_align_warp_kernel<6,dense> (B200ICP_FLAG_DENSE_SWEEP | "
+                                               "B200ICP_FLAG_NO_SWEEP_REUSE: every pair-eval executed in every "
+                                               "iteration; bit-identical poses)", "kernel_ms": dense_ms,
                                      "achieved": flops / (dense_ms * 1e-3) / 1e12,
                                      "frac": flops / (dense_ms * 1e-3) / 1e12 / fp32_peak},
                      "note": "achieved = brute-force-equivalent work (SURVEY.md 8d: N_src x N_tgt x iterations x 5 "
-                             "FLOP) / time.  The sweep prunes target groups that are provably out of reach "
+                             "FLOP) / time.  The sweep prunes target groups that are provably out of reach and a "
+                             "pass skips its sweep while its points provably keep their nearest neighbour's group "
                              "(results identical to the full sweep, DESIGN.md 4.2), so fewer pair-evals are "
-                             "executed: see executed_pair_eval_fraction / executed_tflops.",
+                             "executed -- frac can exceed 1: see executed_pair_eval_fraction / executed_tflops "
+                             "and dense_sweep for the brute-force figure.",
                      "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
                              "algorithmic_bytes_per_launch": P * ALG_BYTES_PER_ALIGNMENT}},

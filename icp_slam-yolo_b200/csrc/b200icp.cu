@@ -71,6 +71,7 @@ struct KernelArgs {
   int32_t mcap;         // tgt_pitch rounded up to kGroup
   int32_t ncap;         // warp kernel: src_pitch rounded up to 32 * SC
   int32_t use_gate;
+  int32_t passes;       // warp kernels: ncap / (32 * sources per lane)
   int32_t reuse;        // fused warp kernel: skip the sweep of a pass while its sources provably keep their group
 };
 
@@ -657,17 +658,23 @@ struct WarpTile {
   float* gcx;           // [mcap/8] bounding circle of each group of 8 targets (pruned sweep)
   float* gcy;
   float* grad;
-  unsigned short* grp;  // [ncap] group of every source's nearest neighbour at its last full sweep
+  unsigned char* grp;   // [src_pitch] group of every source's nearest neighbour at its last full sweep
+                        // (one byte when the targets form <= 256 groups, else two)
+  float* tpass;         // [passes] sweep-reuse thresholds (see WarpCtx::cum_move)
+  bool grp16;
   double ox, oy;
   float tmax;
   int m, mcap, ngroups;
 };
 
-constexpr int kCtxBytes = 400;        // WarpCtx, padded to 16 bytes
-constexpr int kMaxPasses = 32;        // kMaxSrcPitch / 32
-__host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap) {
+// Shared memory of one warp-per-pair CTA.  Every byte counts: at 360 x 360 points 16 CTAs per SM
+// need <= 11,520 B each to stay inside the 196 KB carve-out, which leaves the L1 that the
+// matched-target gathers hit; one more 16-byte granule and the SM falls back to 28 KB of L1.
+constexpr int kCtxBytes = 128;        // WarpCtx
+__host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap, int src_pitch, int passes) {
   const size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
-                   (size_t)(mcap / kGroup) * 3 * sizeof(float) + (size_t)ncap * sizeof(unsigned short);
+                   (size_t)passes * sizeof(float) + (size_t)(mcap / kGroup) * 3 * sizeof(float) +
+                   (size_t)src_pitch * (mcap / kGroup > 256 ? 2 : 1);
   return (b + 15) & ~(size_t)15;
 }
 
@@ -978,9 +985,8 @@ struct WarpCtx {
   double inv_n;
   int iters, inl;
   // sweep reuse: cum_move bounds how far any source point has moved since the start (sum of the
-  // per-iteration maximum displacements); pass q may skip its sweep while cum_move <= tpass[q]
+  // per-iteration maximum displacements); pass q may skip its sweep while cum_move <= tile.tpass[q]
   double cum_move;
-  double tpass[kMaxPasses];
 };
 static_assert(sizeof(WarpCtx) <= kCtxBytes, "WarpCtx outgrew its shared-memory slot");
 
@@ -1009,7 +1015,8 @@ __device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int bas
   if (reuse) {
 #pragma unroll
     for (int k = 0; k < SC; ++k) {
-      c.group[k] = t.grp[base + k * 32 + lane];
+      const int i = base + k * 32 + lane;
+      c.group[k] = i < n ? (t.grp16 ? (int)reinterpret_cast<const unsigned short*>(t.grp)[i] : (int)t.grp[i]) : 0;
       c.best[k] = 0.f; c.second[k] = CUDART_INF_F;        // cross-group guard: settled by the movement bound
     }
   } else if (PRUNE) {
@@ -1084,7 +1091,11 @@ __device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int bas
 #pragma unroll
     for (int k = 0; k < SC; ++k) {
       if ((j[k] >> 3) != c.group[k]) lb[k] = -1.f;       // float64 rescan picked another group: no bound
-      t.grp[base + k * 32 + lane] = (unsigned short)(j[k] >> 3);
+      const int i = base + k * 32 + lane;
+      if (i < n) {
+        if (t.grp16) reinterpret_cast<unsigned short*>(t.grp)[i] = (unsigned short)(j[k] >> 3);
+        else t.grp[i] = (unsigned char)(j[k] >> 3);
+      }
     }
   }
   return evals;
@@ -1097,10 +1108,12 @@ __device__ __forceinline__ void carve_warp_tile(unsigned char* smem, const Kerne
   t.tile = reinterpret_cast<float*>(smem);
   t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);  // 12*mcap bytes, mcap % 8 == 0
   ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
-  t.gcx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + kCtxBytes);
+  t.tpass = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + kCtxBytes);
+  t.gcx = t.tpass + a.passes;
   t.gcy = t.gcx + a.mcap / kGroup;
   t.grad = t.gcy + a.mcap / kGroup;
-  t.grp = reinterpret_cast<unsigned short*>(t.grad + a.mcap / kGroup);
+  t.grp = reinterpret_cast<unsigned char*>(t.grad + a.mcap / kGroup);     // 2-byte aligned: all counts above are even * 4
+  t.grp16 = a.mcap / kGroup > 256;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1192,7 +1205,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
     ctx->iters = 0; ctx->inl = 0;
     ctx->cum_move = 0.0;
   }
-  ctx->tpass[lane] = -CUDART_INF;                 // kMaxPasses == 32: no pass may skip its first sweep
+  if (lane < a.passes) t.tpass[lane] = -CUDART_INF_F;   // passes <= 32: no pass may skip its first sweep
   __syncwarp();
   const bool track = a.reuse != 0;
   int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
@@ -1222,7 +1235,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
         int j[SC];
         float lb[SC];
         const int pass = base / (32 * SC);
-        const bool reuse = track && ctx->cum_move <= ctx->tpass[pass];
+        const bool reuse = track && ctx->cum_move <= (double)t.tpass[pass];
         evals += warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j, reuse, track, lb);
         float budget = CUDART_INF_F;
         // ---- gather (icp.py:39): all SC loads in flight before the first use
@@ -1257,7 +1270,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
         }
         if (track && !reuse) {       // how far the points of this pass may move before it must sweep again
           budget = warp_min_f32(budget);
-          if (lane == 0) ctx->tpass[pass] = budget > 0.f ? ctx->cum_move + 0.999 * (double)budget : -CUDART_INF;
+          if (lane == 0) t.tpass[pass] = budget > 0.f ? __double2float_rd(ctx->cum_move + 0.999 * (double)budget) : -CUDART_INF_F;
         }
       }
 #pragma unroll
@@ -1729,9 +1742,10 @@ WarpShape pick_warp_shape(const b200icp_problem* prob, bool dense, const LaunchS
     }
   }
   args.ncap = (prob->src_pitch + 32 * w.S - 1) / (32 * w.S) * (32 * w.S);
+  args.passes = args.ncap / (32 * w.S);
   ws = ls;
   ws.warps = 1;
-  ws.smem = warp_tile_bytes(ls.mcap, args.ncap);
+  ws.smem = warp_tile_bytes(ls.mcap, args.ncap, prob->src_pitch, args.passes);
   return w;
 }
 
