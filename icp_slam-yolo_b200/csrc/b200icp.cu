@@ -671,10 +671,10 @@ struct WarpTile {
 // need <= 11,520 B each to stay inside the 196 KB carve-out, which leaves the L1 that the
 // matched-target gathers hit; one more 16-byte granule and the SM falls back to 28 KB of L1.
 constexpr int kCtxBytes = 128;        // WarpCtx
-__host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap, int src_pitch, int passes) {
-  const size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
-                   (size_t)passes * sizeof(float) + (size_t)(mcap / kGroup) * 3 * sizeof(float) +
-                   (size_t)src_pitch * (mcap / kGroup > 256 ? 2 : 1);
+__host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap, int src_pitch, int passes, bool reuse) {
+  size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
+             (size_t)passes * sizeof(float) + (size_t)(mcap / kGroup) * 3 * sizeof(float);
+  if (reuse) b += (size_t)src_pitch * (mcap / kGroup > 256 ? 2 : 1);      // grp: the fused loop only
   return (b + 15) & ~(size_t)15;
 }
 
@@ -1207,12 +1207,12 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
   }
   if (lane < a.passes) t.tpass[lane] = -CUDART_INF_F;   // passes <= 32: no pass may skip its first sweep
   __syncwarp();
-  const bool track = a.reuse != 0;
   int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
   long long evals = 0;          // pair evaluations executed by the sweep (padded targets included)
 
   if (ran) {
     warp_stage_targets(t, lane);
+    float smax = 0.f;          // bound of |s - c| over the source points, c = target centroid (sweep reuse)
     for (int i = lane; i < a.ncap; i += 32) {
       double2 v = make_double2(t.ox, t.oy);                // padding slots: benign, never used
       if (i < n) {
@@ -1221,21 +1221,29 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
         if (op.init_pose)
           v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
                            ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
+        smax = fmaxf(smax, fmaxf(__double2float_ru(fabs(v.x - t.ox)), __double2float_ru(fabs(v.y - t.oy))));
       }
       t.src[i] = v;
     }
+    smax = warp_max_f32(smax) * 1.4142137f;
+    float mv_prev = CUDART_INF_F;      // displacement bound of the previous update
+    double err_prev = 0.0;
     __syncwarp();
 
     for (int it = 0; it < op.max_iterations; ++it) {       // icp.py:35
       int32_t* hist = out.index_history
           ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
       double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      // Sweep reuse.  A pass reuses its stored groups whenever the movement bound allows it; the
+      // sweeps compute new bounds (lb, budgets) only once the last update moved the points by less
+      // than half the mean NN distance -- before that no budget would survive the next update.
+      const bool track = a.reuse != 0 && (double)mv_prev < 0.5 * err_prev;
       for (int base = 0; base < n; base += 32 * SC) {
         // ---- correspondence search for the SC sources of every lane (icp.py:37-38)
         int j[SC];
         float lb[SC];
         const int pass = base / (32 * SC);
-        const bool reuse = track && ctx->cum_move <= (double)t.tpass[pass];
+        const bool reuse = a.reuse != 0 && ctx->cum_move <= (double)t.tpass[pass];
         evals += warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j, reuse, track, lb);
         float budget = CUDART_INF_F;
         // ---- gather (icp.py:39): all SC loads in flight before the first use
@@ -1255,7 +1263,7 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
             const double2 b = bm[k];
             const double d2 = dist2_f64(s.x, s.y, b);
             const double dist = sqrt_f64_fast(d2);
-            budget = fminf(budget, 0.5f * (lb[k] - __double2float_ru(dist) * 1.000001f));
+            if (track && !reuse) budget = fminf(budget, 0.5f * (lb[k] - __double2float_ru(dist) * 1.000001f));
             if (!use_gate || dist < gate) {
               const double ax = s.x - t.ox, ay = s.y - t.oy;
               const double qx = b.x - t.ox, qy = b.y - t.oy;
@@ -1301,16 +1309,26 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
       const double cax = t.ox + max_, cay = t.oy + may_;
       const double tx = (t.ox + mbx) - (cs * cax - sn * cay);  // icp.py:25
       const double ty = (t.oy + mby) - (sn * cax + cs * cay);
-      double mv2 = 0.0;
       for (int i = lane; i < n; i += 32) {                     // apply (icp.py:45)
         const double2 s = t.src[i];
-        const double2 v = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
-        t.src[i] = v;
-        const double mx = v.x - s.x, my = v.y - s.y;
-        mv2 = fmax(mv2, fma(mx, mx, my * my));
+        t.src[i] = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
       }
+      // Upper bound of every point's displacement in this update (sweep reuse): with c the target
+      // centroid, s' - s = (R - I)(s - c) + [(R - I) c + t], so |s' - s| <= |R - I| * smax + |(R - I) c + t|
+      // with |R - I| = sqrt((cos - 1)^2 + sin^2) and smax >= |s - c| for every point (initial maximum,
+      // grown by every displacement bound since).  Rounded up, plus the rounding of the update itself
+      // (a few ulp of the coordinates).  Identical in every lane.
       float mv = 0.f;
-      if (track) mv = warp_max_f32(__fsqrt_ru(__double2float_ru(mv2)));   // largest displacement, rounded up
+      if (a.reuse) {
+        const double c1 = cs - 1.0;
+        const double rho = sqrt(fma(c1, c1, sn * sn));
+        const double ddx = fma(c1, t.ox, -sn * t.oy) + tx, ddy = fma(sn, t.ox, c1 * t.oy) + ty;
+        const double ulp = 1.0e-15 * (fabs(t.ox) + fabs(t.oy) + (double)smax + fabs(tx) + fabs(ty));
+        mv = __double2float_ru((rho * (double)smax + sqrt(fma(ddx, ddx, ddy * ddy))) * 1.000001 + ulp);
+        smax = __fadd_ru(smax, mv);
+        mv_prev = mv;
+        err_prev = mean_error;
+      }
       const bool converged = fabs(ctx->prev_error - mean_error) < op.tolerance;   // icp.py:49-50
       __syncwarp();
       if (lane == 0) {            // compose the cumulative pose, record the increment
@@ -1745,7 +1763,7 @@ WarpShape pick_warp_shape(const b200icp_problem* prob, bool dense, const LaunchS
   args.passes = args.ncap / (32 * w.S);
   ws = ls;
   ws.warps = 1;
-  ws.smem = warp_tile_bytes(ls.mcap, args.ncap, prob->src_pitch, args.passes);
+  ws.smem = warp_tile_bytes(ls.mcap, args.ncap, prob->src_pitch, args.passes, args.reuse != 0);
   return w;
 }
 
