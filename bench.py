@@ -294,7 +294,7 @@ def run_b200(args):
     # ---- e2e: pinned host buffers -> chunked H2D || kernel || D2H, through HostPipeline
     e2e = None
     if not args.no_e2e:
-        n_chunks = int(os.environ.get("B200ICP_E2E_CHUNKS", "4"))
+        n_chunks = int(os.environ.get("B200ICP_E2E_CHUNKS", "8"))
         pipe = m.registration.HostPipeline(P, N_POINTS, N_POINTS, dtype=torch.float32, chunks=n_chunks, device=dev)
         for _ in range(2):
             pipe.run(h_src, h_tgt, max_iterations=ITERS, tolerance=-1.0)

@@ -307,18 +307,20 @@ class HostPipeline:
     makes.  Pinned host tables are streamed to the device in chunks on a copy stream while
     the previous chunk's ICP kernel runs, and each chunk's poses / errors / iteration counts
     are copied back to pinned host memory, so host<->device traffic overlaps the compute.
+    Consecutive chunks run on two alternating compute streams: the next chunk's CTAs fill the SMs
+    that the tail wave of the current chunk leaves idle.
 
     Device staging buffers and pinned result buffers are allocated once and reused.
     """
 
     def __init__(self, n_pairs: int, src_pitch: int, tgt_pitch: int, dtype=torch.float32,
-                 chunks: int = 4, device="cuda"):
+                 chunks: int = 8, device="cuda"):
         self.n_pairs, self.src_pitch, self.tgt_pitch = int(n_pairs), int(src_pitch), int(tgt_pitch)
         self.device = torch.device(device)
         self.chunk = max(1, -(-self.n_pairs // max(1, chunks)))
-        # chunk boundaries: a short first chunk (1/4 of a regular one) so that the exposed part of
+        # chunk boundaries: a short first chunk (1/8 of a regular one) so that the exposed part of
         # the pipeline -- the first host-to-device copy -- is small; the rest are regular
-        first = max(1, self.chunk // 4)
+        first = max(1, self.chunk // 8)
         self.bounds = [0, min(first, self.n_pairs)]
         while self.bounds[-1] < self.n_pairs:
             self.bounds.append(min(self.n_pairs, self.bounds[-1] + self.chunk))
@@ -330,6 +332,7 @@ class HostPipeline:
                           out=alloc_outputs(c, src_pitch, self.device)) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.out_stream = torch.cuda.Stream(device=self.device)
+        self.compute_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.h_pose = pin(self.n_pairs, 6, dt=torch.float64)
         self.h_error = pin(self.n_pairs, dt=torch.float64)
@@ -365,16 +368,20 @@ class HostPipeline:
                     buf["tlen"][:nb].copy_(h_tgt_len[b0:b1], non_blocking=True)
                 copied = torch.cuda.Event()
                 copied.record(self.copy_stream)
-            main.wait_event(copied)
+            cs = self.compute_streams[ci & 1]
+            if ci < 2:
+                cs.wait_stream(main)                                # work queued by the caller before run()
+            cs.wait_event(copied)
             if drained[ci & 1] is not None:
-                main.wait_event(drained[ci & 1])                    # previous results left the buffer
+                cs.wait_event(drained[ci & 1])                      # previous results left the buffer
             s = ScanTable(buf["src"][:nb], buf["slen"][:nb] if h_src_len is not None else None)
             t = ScanTable(buf["tgt"][:nb], buf["tlen"][:nb] if h_tgt_len is not None else None)
-            align_pairs(s, t, n_pairs=nb, max_iterations=max_iterations, tolerance=tolerance,
-                        max_corr_dist=max_corr_dist, out=buf["out"], stream=main)
+            with torch.cuda.stream(cs):
+                align_pairs(s, t, n_pairs=nb, max_iterations=max_iterations, tolerance=tolerance,
+                            max_corr_dist=max_corr_dist, out=buf["out"], stream=cs)
             self.launches += 1
             done = torch.cuda.Event()
-            done.record(main)
+            done.record(cs)
             ready[ci & 1] = done
             with torch.cuda.stream(self.out_stream):
                 self.out_stream.wait_event(done)
