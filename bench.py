@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="pairs", choices=["pairs", "odometry", "allpairs", "scan2map", "nn", "occupancy"],
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "odometry", "allpairs", "scan2map", "nn", "occupancy", "slam"],
                     help="pairs = the headline configs[2] (default); the others are BASELINE.json "
                          "configs[1], [3] and [4], reported with the same JSON shape")
     ap.add_argument("--map-points", type=int, default=1 << 24, help="scan2map: total map points")
@@ -773,6 +773,60 @@ def run_occupancy(args):
     print(json.dumps(line), flush=True)
 
 
+def run_slam(args):
+    """The reference's offline SLAM loop (duc/ICP_LIDAR/slam_offline.py:318-455) composed from the
+    device primitives (icp_slam-yolo_b200/slam.py) over the first 400 scans of the bundled
+    recording: per frame local-map crop, voxel grids, gated scan-to-map ICP with the previous pose,
+    dynamic-point removal, occupancy filter, map growth / re-sampling, ray casting, pruning.  The
+    loop is host-driven and sequential (every frame needs the previous pose), so the metric is
+    wall-clock frames per second around the whole loop, device synchronised at both ends.  CPU
+    leg: the same composition of the CPU oracles (oracle/slam_oracle.py), one core."""
+    import torch
+    import icp_slam_yolo_b200 as m
+    from icp_slam_yolo_b200.slam import OfflineSlam, SlamConfig
+    from oracle import icp_oracle as orc
+    from oracle.slam_oracle import OracleSlam
+    FRAMES = 400
+    raw = _fixture_scans()[2:2 + FRAMES]
+    scans = []
+    for r in raw:
+        xy = orc.polar_to_cartesian(r)
+        scans.append(np.ascontiguousarray(xy))
+    t0 = time.perf_counter()
+    ora = OracleSlam(SlamConfig())
+    ora.first(scans[0])
+    o_acc = sum(int(bool(o and o[0])) for o in (ora.step(s) for s in scans[1:]))
+    cpu_wall = time.perf_counter() - t0
+    torch.cuda.set_device(0)
+    walls = []
+    for it in range(1 + args.steps):                     # first pass = warm-up
+        dev = OfflineSlam(SlamConfig())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = dev.run(scans)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    wall = min(walls[1:])
+    acc = sum(int(bool(r and r.accepted)) for r in res)
+    same = bool(np.array_equal(dev.grid.probs_numpy().view(np.uint32), ora.occ.view(np.uint32)) and
+                np.allclose(dev.global_pose, ora.pose, atol=1e-6) and acc == o_acc)
+    line = {
+        "metric": "offline SLAM loop frames/sec (Scan_data_1, first %d scans)" % FRAMES,
+        "value": (FRAMES - 1) / wall, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": 1,
+        "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "replicas", "vs_baseline": None,
+        "dtype": "f32 search + f64 state; f32 occupancy", "data": "bundled recording (fixture)",
+        "config": {"workload": "slam_offline.py:318-455 composed from the device primitives; host-driven, sequential",
+                   "frames": FRAMES, "accepted": acc, "map_points": int(dev.global_map.shape[0])},
+        "matches_oracle_composition": same,
+        "cpu_baseline": {"value": (FRAMES - 1) / cpu_wall, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": f"the same {FRAMES} frames through oracle/slam_oracle.py (NumPy/SciPy + C occupancy), "
+                                   f"{cpu_wall:.2f} s; {cpu_model()}"},
+        "note": "launch- and synchronisation-bound (a dozen small launches and three device-to-host reads per "
+                "frame); reported for completeness, not a roofline workload",
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -787,6 +841,8 @@ def main():
         run_nn(args)
     elif args.workload == "occupancy":
         run_occupancy(args)
+    elif args.workload == "slam":
+        run_slam(args)
     else:
         run_b200(args)
     try:

@@ -111,3 +111,24 @@ def test_against_live_reference_when_present():
         occ.update_occupancy_map_c(o_o, i_o, pts[f], rob[f], (160, 150), 30)
     del ref.update_occupancy_map.occupancy_probs
     assert np.array_equal(o_r.view(np.uint32), o_o.view(np.uint32)) and np.array_equal(i_r, i_o)
+
+
+def test_slam_oracle_composition_tracks_the_recording(packed):
+    """oracle/slam_oracle.py (the order of slam_offline.py:318-455 over the pinned oracles): the
+    first 80 scans are all registered, the map grows and is re-sampled, free space is carved."""
+    from oracle import icp_oracle as orc
+    from oracle.slam_oracle import OracleSlam
+
+    class Cfg:                                   # duc/ICP_LIDAR/Config.py:7-21
+        resolution_mm_per_pixel = 30; map_width_pixels = 1000; map_height_pixels = 833
+        icp_voxel_size = 25.0; icp_threshold = 180.0; max_rmse_threshold = 50.0
+        dynamic_distance_threshold = 300.0; local_map_radius_mm = 9000.0; min_icp_map_points = 50
+        max_map_points_before_downsample = 1000; min_scan_points = 10; max_iteration = 50; tolerance = 1e-5
+
+    scans = [orc.polar_to_cartesian(occ.unpack_scan(packed, f)) for f in range(2, 82)]
+    slam = OracleSlam(Cfg)
+    slam.first(scans[0])
+    out = [slam.step(s) for s in scans[1:]]
+    assert all(o is not None and o[0] and o[1] < 50.0 for o in out)
+    assert len(slam.map) > 1000 and np.hypot(*slam.pose[:2, 3]) > 20.0
+    assert slam.occ.max() >= 0.65 and slam.occ.min() < 0.2
