@@ -38,7 +38,7 @@ extern "C" {
 #endif
 
 #define B200ICP_VERSION_MAJOR 0
-#define B200ICP_VERSION_MINOR 1
+#define B200ICP_VERSION_MINOR 2   /* 0.2: occupancy-grid entry points, sweep-reuse flag */
 
 typedef enum b200icp_status {
   B200ICP_OK = 0,
