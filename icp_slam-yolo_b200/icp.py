@@ -144,19 +144,36 @@ def registration_p2p(points1, points2, threshold: float = 200.0, voxel_size: Opt
     ``icp(...)`` in duc/code python/b.py:219-236, including the ``< 10`` points guard
     (gicp_lidar.py:13-15).  Gate / rmse semantics are parity-unpinned (Open3D is not
     vendored by the reference) and are defined by oracle.icp_oracle.icp_extended.
+    ``points1`` / ``points2`` may be NumPy arrays or CUDA tensors ((N, 2) or (N, 3)); tensors stay
+    on the device from the voxel grid to the pose (the SLAM loop passes its map that way).
     """
-    p1 = np.asarray(points1, dtype=np.float64)
-    p2 = np.asarray(points2, dtype=np.float64)
-    if len(p1) < 10 or len(p2) < 10:
+    if len(points1) < 10 or len(points2) < 10:
         return float("inf"), np.eye(4)
+
+    def dev(p):
+        if isinstance(p, torch.Tensor):
+            t = p[:, :2].to(device="cuda", dtype=torch.float64)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(p, dtype=np.float64)[:, :2])).cuda()
+        return t.contiguous()
+
+    p1, p2 = dev(points1), dev(points2)
     if voxel_size:                       # gicp_lidar.py:20-21: both clouds are down-sampled first
         from .mapping import voxel_down_sample
-        p1 = voxel_down_sample(torch.from_numpy(np.ascontiguousarray(p1[:, :2])).cuda(), voxel_size).cpu().numpy()
-        p2 = voxel_down_sample(torch.from_numpy(np.ascontiguousarray(p2[:, :2])).cuda(), voxel_size).cpu().numpy()
-    o = icp_full(p1, p2, max_iteration, tolerance,
-                 init_pose=None if trans_init is None else np.asarray(trans_init),
-                 max_corr_dist=threshold)
+        p1, p2 = voxel_down_sample(p1, voxel_size), voxel_down_sample(p2, voxel_size)
+    lib = _cabi.lib()
+    if p1.shape[0] > lib.b200icp_max_src_pitch() or p2.shape[0] > lib.b200icp_max_tgt_pitch():
+        o = _icp_full_large(p1.cpu().numpy(), p2.cpu().numpy(), max_iteration, tolerance,
+                            None if trans_init is None else np.asarray(trans_init), threshold)
+        rmse, R, t = o.rmse, o.R, o.t
+    else:
+        res = align_pairs(ScanTable(p1[None].contiguous()), ScanTable(p2[None].contiguous()), n_pairs=1,
+                          max_iterations=max_iteration, tolerance=tolerance,
+                          init_pose=None if trans_init is None else _pose6(np.asarray(trans_init)),
+                          max_corr_dist=threshold)
+        host = torch.cat([res.pose_total[0], res.rmse]).cpu().numpy()       # one device-to-host read
+        R, t, rmse = host[:4].reshape(2, 2), host[4:6], float(host[6])
     T = np.eye(4)
-    T[:2, :2] = o.R
-    T[:2, 3] = o.t
-    return o.rmse, T
+    T[:2, :2] = R
+    T[:2, 3] = t
+    return rmse, T

@@ -112,7 +112,7 @@ class OfflineSlam:
             map_for_icp = crop_local_map(self.global_map, robot[:2], c.local_map_radius_mm, c.min_icp_map_points)
         else:
             map_for_icp = self.global_map
-        rmse, T = registration_p2p(current_points, map_for_icp.cpu().numpy(), c.icp_threshold, c.icp_voxel_size,
+        rmse, T = registration_p2p(current_points, map_for_icp, c.icp_threshold, c.icp_voxel_size,
                                    trans_init=self.global_pose, max_iteration=c.max_iteration,
                                    tolerance=c.tolerance)                                   # :382
         if rmse > c.max_rmse_threshold:                                                     # :386-387: `continue`
