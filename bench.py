@@ -470,9 +470,10 @@ def run_odometry(args):
                                "tolerance 1e-5, ragged 11..196 points", "iterations_total": gpu_its,
                    "l2": "inputs (5.7 MB) fit L2: a 64 MB buffer is NOT flushed between steps; noted"},
         "gpu_launches": args.steps,
-        "roofline": {"bound": "fp32", "kernel": "icp_align_warp_kernel", "achieved": evals * 5 / (ms * 1e-3) / 1e12,
+        "roofline": {"bound": "fp32", "kernel": "icp_align_kernel (CTA per pair: the dispatcher's choice up to 2,048 pairs)",
+                     "achieved": evals * 5 / (ms * 1e-3) / 1e12,
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": evals * 5 / (ms * 1e-3) / 1e12 / fp32_peak,
-                     "traffic": None, "note": "tiny ragged problems: 1,830 one-warp CTAs = 0.77 waves"},
+                     "traffic": None, "note": "tiny ragged problems, less than one wave: bound by the latency of the longest pair"},
         "e2e": {"value": n_pairs / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h_raw.numel() * 8 + h_len.numel() * 4),
                 "d2h_bytes_per_step": n_pairs * 48,

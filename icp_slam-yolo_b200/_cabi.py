@@ -18,6 +18,8 @@ F32, F64 = 0, 1
 PAIR_ROWWISE, PAIR_EXPLICIT, PAIR_TRIANGLE = 0, 1, 2
 FLAG_DENSE_SWEEP = 1
 FLAG_NO_SWEEP_REUSE = 2
+FLAG_WARP_KERNEL = 4
+FLAG_CTA_KERNEL = 8
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "CUDA", 4: "NO_DEVICE"}
 

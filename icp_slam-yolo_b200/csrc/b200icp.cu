@@ -38,6 +38,7 @@ constexpr int kMaxWarps = 8;       // CTA size limit of the per-pair kernels
 constexpr int kMaxS = 4;           // source points per lane
 constexpr int kMaxSrcPitch = kMaxS * kMaxWarps * 32;   // 1024
 constexpr int kMaxTgtPitch = 4096;
+constexpr int64_t kAutoCtaPairs = 2048;   // at or below: CTA-per-pair fused kernel (latency), above: warp-per-pair (throughput)
 constexpr int kRedStride = 8;      // doubles per warp slot in the staging reductions
 constexpr int kRedStride2 = 12;    // doubles per warp slot in the per-iteration reduction
 constexpr unsigned kFull = 0xffffffffu;
@@ -1859,7 +1860,17 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   args.use_gate = (opt->max_corr_dist > 0.0 && std::isfinite(opt->max_corr_dist)) ? 1 : 0;
   args.reuse = (env_int("B200ICP_REUSE", 1) != 0 && !(opt->flags & B200ICP_FLAG_NO_SWEEP_REUSE)) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (env_int("B200ICP_ALIGN_BLOCK", 0) == 0) {
+  // Which fused kernel?  One warp per pair has the best throughput once the pairs fill the GPU
+  // (148 SMs x 16 one-warp CTAs); below that a pair's latency is what counts and the CTA-per-pair
+  // kernel (up to 8 warps on one pair) is 2-4.6x faster: 0.14 vs 0.52 ms for one 160 x 1,000
+  // scan-to-local-map registration, crossover near 1,000 pairs of 360 x 360 (tools/latency_single.py).
+  int cta = -1;
+  if (opt->flags & B200ICP_FLAG_WARP_KERNEL) cta = 0;
+  else if (opt->flags & B200ICP_FLAG_CTA_KERNEL) cta = 1;
+  else cta = env_int("B200ICP_ALIGN_BLOCK", -1);
+  if (cta < 0)
+    cta = (n_pairs <= kAutoCtaPairs && !(opt->flags & B200ICP_FLAG_DENSE_SWEEP) && !out->evaluated_pairs) ? 1 : 0;
+  if (cta == 0) {
     const bool dense = env_int("B200ICP_PRUNE", 1) == 0 || (opt->flags & B200ICP_FLAG_DENSE_SWEEP);
     B200ICP_DISPATCH_WARP(icp_align_warp_kernel, dense)
   }

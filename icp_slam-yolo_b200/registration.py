@@ -211,7 +211,7 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
                 init_pose: Optional[torch.Tensor] = None, max_corr_dist: Optional[float] = None,
                 want_indices: bool = False, want_src: bool = False, want_history: bool = False,
                 want_stats: bool = False, dense_sweep: bool = False, sweep_reuse: bool = True,
-                out: Optional[AlignResult] = None, stream=None) -> AlignResult:
+                kernel: str = "auto", out: Optional[AlignResult] = None, stream=None) -> AlignResult:
     """Run the whole ICP loop of every pair on the device (one kernel launch).
 
     Replaces ``icp(A, B, max_iterations, tolerance)`` (icp.py:28-53) for a batch:
@@ -221,6 +221,8 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     provably out of reach (identical results; only worth it for spatially unordered point sets).
     ``sweep_reuse=False`` sweeps every pass in every iteration instead of skipping the sweep of a
     pass whose points provably keep their nearest neighbour's group (identical results; A/B knob).
+    ``kernel``: "auto" (CTA-per-pair fused kernel up to 2,048 pairs -- lowest latency --, warp-per-pair
+    above -- highest throughput), "warp" or "cta".
     """
     pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
     b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
@@ -231,7 +233,8 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
                             want_stats=want_stats)
     opt = _cabi.Options()
     opt.max_iterations = int(max_iterations)
-    opt.flags = (_cabi.FLAG_DENSE_SWEEP if dense_sweep else 0) | (0 if sweep_reuse else _cabi.FLAG_NO_SWEEP_REUSE)
+    opt.flags = ((_cabi.FLAG_DENSE_SWEEP if dense_sweep else 0) | (0 if sweep_reuse else _cabi.FLAG_NO_SWEEP_REUSE) |
+                 {"auto": 0, "warp": _cabi.FLAG_WARP_KERNEL, "cta": _cabi.FLAG_CTA_KERNEL}[kernel])
     opt.tolerance = float(tolerance)
     opt.max_corr_dist = 0.0 if max_corr_dist is None else float(max_corr_dist)
     if init_pose is not None:

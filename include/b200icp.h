@@ -97,6 +97,13 @@ typedef struct b200icp_problem {
                                           since then against the gap to the nearest outside target);
                                           the correspondences are identical either way.            */
 
+#define B200ICP_FLAG_WARP_KERNEL 4  /* force the warp-per-pair fused kernel                         */
+#define B200ICP_FLAG_CTA_KERNEL 8   /* force the CTA-per-pair fused kernel.  Default: chosen by the
+                                       batch size -- one warp per pair has the higher throughput once
+                                       the pairs fill the GPU (> 2,048), a CTA of up to 8 warps per pair
+                                       the lower latency below that (one registration per frame).
+                                       Identical correspondences; poses agree to ~1e-12.          */
+
 typedef struct b200icp_options {
   int32_t max_iterations;   /* icp.py:28,35; reference default 20                   */
   int32_t flags;            /* B200ICP_FLAG_*                                        */

@@ -156,12 +156,15 @@ def test_circle_demo_known_answer(b200, golden):
     assert np.allclose(src, golden["demo_A_aligned"], atol=1e-12) and R.shape == (2, 2) and t.shape == (2,)
 
 
-def test_scan_data_1_all_pairs_full_history(b200, cart_scans, oracle_pairs, golden):
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_scan_data_1_all_pairs_full_history(b200, cart_scans, oracle_pairs, golden, kernel):
     """Config 2: all 1,830 consecutive pairs in one launch; every iteration's correspondence
     vector, the iteration count, the pose and the error against the oracle; the pose also
-    against what the unmodified reference produced (golden fixture)."""
+    against what the unmodified reference produced (golden fixture).  Both fused kernels: the
+    dispatcher picks the CTA-per-pair one for a batch of this size, the warp-per-pair one above
+    2,048 pairs."""
     table = b200.ScanTable.from_list(cart_scans)
-    res = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5,
+    res = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5, kernel=kernel,
                                  want_indices=True, want_src=True, want_history=True)
     torch.cuda.synchronize()
     for p, o in enumerate(oracle_pairs):
@@ -335,12 +338,13 @@ def test_reference_shaped_wrappers(b200, cart_scans):
 # every kernel variant, adversarial shapes for the pruned sweep
 # ---------------------------------------------------------------------------------------
 _VARIANTS = {
-    "warp-pruned": {},
-    "warp-pruned-S1": {"B200ICP_PRUNE_S": "1"},
-    "warp-pruned-S4": {"B200ICP_PRUNE_S": "4"},
-    "warp-dense": {"B200ICP_PRUNE": "0"},
-    "warp-pruned-no-reuse": {"B200ICP_REUSE": "0"},
-    "warp-dense-no-reuse": {"B200ICP_PRUNE": "0", "B200ICP_REUSE": "0"},
+    "auto": {},
+    "warp-pruned": {"B200ICP_ALIGN_BLOCK": "0"},
+    "warp-pruned-S1": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE_S": "1"},
+    "warp-pruned-S4": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE_S": "4"},
+    "warp-dense": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE": "0"},
+    "warp-pruned-no-reuse": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_REUSE": "0"},
+    "warp-dense-no-reuse": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE": "0", "B200ICP_REUSE": "0"},
     "block-expanded": {"B200ICP_ALIGN_BLOCK": "1"},
     "block-direct": {"B200ICP_ALIGN_BLOCK": "1", "B200ICP_SEARCH_DIRECT": "1"},
 }
