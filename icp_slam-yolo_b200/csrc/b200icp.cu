@@ -1830,7 +1830,10 @@ int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs, int32_t* idx_
     case 8: return launch_pairs(KERNEL<4, false>, ls, args, st);                       \
     default: return launch_pairs(KERNEL<4, true>, ls, args, st);                       \
   }
-  if (env_int("B200ICP_NN_BLOCK", 0) == 0) {
+  // same rule as the fused loop: CTA per pair below the batch size that fills the GPU with one-warp CTAs
+  int cta = env_int("B200ICP_NN_BLOCK", -1);
+  if (cta < 0) cta = n_pairs <= kAutoCtaPairs ? 1 : 0;
+  if (cta == 0) {
     const bool dense = env_int("B200ICP_PRUNE", 1) == 0;
     B200ICP_DISPATCH_WARP(nn_warp_kernel, dense)
   }

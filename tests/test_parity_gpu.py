@@ -68,7 +68,9 @@ def _check_pair(res, p, o, n, *, history=True, rot=TIGHT_ROT, trans=TIGHT_TRANS)
 # ---------------------------------------------------------------------------------------
 # nearest-neighbour kernel (icp.py:37-38)
 # ---------------------------------------------------------------------------------------
-def test_nn_first_iteration_all_scan_pairs_bit_exact(b200, cart_scans):
+@pytest.mark.parametrize("nn_block", ["0", "1"])
+def test_nn_first_iteration_all_scan_pairs_bit_exact(b200, cart_scans, monkeypatch, nn_block):
+    monkeypatch.setenv("B200ICP_NN_BLOCK", nn_block)          # warp-per-pair and CTA-per-pair search kernels
     table = b200.ScanTable.from_list(cart_scans)
     idx, d2 = b200.nn_search(table.slice_rows(1), table.slice_rows(0, table.rows - 1))
     idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
@@ -102,7 +104,8 @@ def test_nn_near_ties_and_exact_ties(b200):
         assert np.array_equal(idx[0, :len(src)].cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("nn_variant", [{}, {"B200ICP_PRUNE": "0"}, {"B200ICP_NN_BLOCK": "1"},
+@pytest.mark.parametrize("nn_variant", [{}, {"B200ICP_NN_BLOCK": "0"}, {"B200ICP_NN_BLOCK": "0", "B200ICP_PRUNE": "0"},
+                                        {"B200ICP_NN_BLOCK": "1"},
                                         {"B200ICP_NN_BLOCK": "1", "B200ICP_SEARCH_DIRECT": "1"}])
 def test_nn_shapes_ragged_and_limits(b200, monkeypatch, nn_variant):
     for k, v in nn_variant.items():
@@ -514,10 +517,12 @@ def test_icp_drop_in_handles_large_sets(b200):
     assert abs(g.fitness - og.fitness) < 1e-12
 
 
-def test_nn_randomised_stress_exact_indices(b200):
+@pytest.mark.parametrize("nn_block", ["0", "1"])
+def test_nn_randomised_stress_exact_indices(b200, monkeypatch, nn_block):
     """2,400 random ragged problems: clustered, lattice (exact ties -> lowest index), collinear,
     duplicated, huge offsets (1e6) and tiny scales (1e-3): the pruned FP32 sweep + float64
     re-decision must equal the float64 brute-force argmin everywhere."""
+    monkeypatch.setenv("B200ICP_NN_BLOCK", nn_block)
     rng = np.random.default_rng(2024)
     A, B = [], []
     for q in range(2400):
