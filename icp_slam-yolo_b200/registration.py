@@ -336,6 +336,9 @@ class HostPipeline:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.out_stream = torch.cuda.Stream(device=self.device)
         self.compute_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        # one fused kernel for every chunk, chosen on the size of the whole batch: results must not
+        # depend on how the batch is cut (the two kernels agree to ~1e-12, not bit for bit)
+        self.kernel = "warp" if self.n_pairs > 2048 else "cta"
         pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.h_pose = pin(self.n_pairs, 6, dt=torch.float64)
         self.h_error = pin(self.n_pairs, dt=torch.float64)
@@ -381,7 +384,7 @@ class HostPipeline:
             t = ScanTable(buf["tgt"][:nb], buf["tlen"][:nb] if h_tgt_len is not None else None)
             with torch.cuda.stream(cs):
                 align_pairs(s, t, n_pairs=nb, max_iterations=max_iterations, tolerance=tolerance,
-                            max_corr_dist=max_corr_dist, out=buf["out"], stream=cs)
+                            max_corr_dist=max_corr_dist, kernel=self.kernel, out=buf["out"], stream=cs)
             self.launches += 1
             done = torch.cuda.Event()
             done.record(cs)
