@@ -22,6 +22,8 @@ empty ``open3d`` stub in place for the import) and these functions are called:
                                                           outside the map, empty inputs, non-default
                                                           parameters
   filter_new_points_by_occupancy    process.py:203-226   seeded points over preset grids
+  polar_to_cartesian_3d             process.py:38-52     all 1,831 scans of Scan_data_1: point count and
+                                                          CRC32 of the float64 output
 
 The inputs of (b) and of the filter cases are stored with the outputs; the inputs of (a) are
 re-derived by the tests from scan_data_1_packed.npz and the stored per-frame poses with
@@ -175,6 +177,19 @@ def main():
         out[f"filter_{i}_par"] = np.asarray([center[0], center[1], res, thr.get("free_threshold", 0.2)])
         out[f"filter_{i}_kept"] = kept
     out["filter_count"] = np.int32(6)
+
+    # ---- polar_to_cartesian_3d (process.py:38-52) on every scan of the recording --------------
+    # (the registration goldens were produced through the oracle's restatement of this function;
+    # here the unmodified function itself is recorded: point count and CRC32 of its output bytes)
+    n_scans = len(packed["offsets"]) - 1
+    p2c_n = np.zeros(n_scans, dtype=np.int32)
+    p2c_crc = np.zeros(n_scans, dtype=np.uint32)
+    for f in range(n_scans):
+        pts = ref.polar_to_cartesian_3d(occ_orc.unpack_scan(packed, f))
+        p2c_n[f] = len(pts)
+        p2c_crc[f] = crc(np.asarray(pts, dtype=np.float64)) if len(pts) else 0
+    out["p2c_count"] = p2c_n
+    out["p2c_crc32"] = p2c_crc
 
     path = os.path.join(HERE, "reference_occupancy_golden.npz")
     np.savez_compressed(path, **out)

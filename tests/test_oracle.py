@@ -1,5 +1,6 @@
 """CPU: the oracle restatement against the reference's golden vectors (parity pin)."""
 import math
+import os
 import zlib
 
 import numpy as np
@@ -152,3 +153,21 @@ def test_c_oracle_matches_numpy_oracle(cart_scans):
     idx, d2 = c_oracle.nn_bruteforce(A, B)
     d, i = orc.nn_kdtree(A, B)
     assert np.array_equal(idx, i) and np.allclose(np.sqrt(d2), d, rtol=1e-15)
+
+
+def test_polar_to_cartesian_restatement_matches_recorded_reference(raw_scans):
+    """process.py:38-52: the UNMODIFIED polar_to_cartesian_3d was run on all 1,831 scans of
+    Scan_data_1 (tests/golden/make_golden_occupancy.py, process.py imported with a stub open3d);
+    point counts and CRC32 of its float64 output must equal the oracle's vectorised and loop
+    restatements bit for bit."""
+    import zlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_occupancy_golden.npz"))
+    assert len(raw_scans) == len(g["p2c_count"]) == 1831
+    for f, raw in enumerate(raw_scans):
+        v = orc.polar_to_cartesian(raw)
+        assert len(v) == int(g["p2c_count"][f]), f"scan {f}"
+        if len(v):
+            assert zlib.crc32(np.ascontiguousarray(v).tobytes()) == int(g["p2c_crc32"][f]), f"scan {f}"
+        if f % 97 == 0:
+            l = orc.polar_to_cartesian_loop(raw)
+            assert np.array_equal(np.asarray(l).reshape(-1, 3), v), f"scan {f} (loop form)"
