@@ -10,15 +10,18 @@
 // cell >= 0.65 (which ends the ray before its end cell is raised), the end cell is raised by
 // p_occ_inc, and adjacent beams share most of their first ~50 cells.  Exactness therefore
 // fixes the order of the beams of one map; what is parallel is
-//   (1) the geometry: every thread of the CTA converts end points to cells and expands the
-//       rays into per-beam cell lists in shared memory (closed form of the reference's
-//       Bresenham walk, no serial stepping);
-//   (2) the cells of one ray: distinct by construction, so one warp reads all of them at once
-//       (up to 160 loads in flight), finds the first blocking cell with a ballot and writes the
-//       cells before it -- one memory round trip per beam instead of one per cell;
-//   (3) the grey-level rendering of the window, all threads;
+//   (1) the geometry: the threads of the CTA convert end points to cells, and 12 producer warps
+//       expand the rays into cell lists (closed form of the reference's Bresenham walk, no serial
+//       stepping) in a shared-memory ring, ahead of the ordered loop;
+//   (2) the cells of one ray: distinct by construction, so the ordered warp reads all of them at
+//       once (128 per trip) from a shared-memory tile of the map, finds the first blocking cell with
+//       a vote and writes the cells before it -- one shared-memory round trip per ray instead of
+//       one global-memory round trip per cell;
+//   (3) the grey-level rendering: only the cells that leave the window per frame, the last window
+//       once per launch, all threads;
 //   (4) independent maps (recordings / robots): one CTA per map, any number of frames per
 //       launch, applied in order.
+// DESIGN.md 4.5d has the measurements and what was tried and rejected.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -32,7 +35,7 @@ namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kOccThreads = 512;
-constexpr int kOccUnroll = 5;                 // 5 x 32 cells per trip covers area <= 159 in one
+constexpr int kOccUnroll = 5;                 // on-map fallback: 5 x 32 cells per trip
 constexpr int kOccTileCells = 54 * 1024;      // float32 map cells held in shared memory (216 KB)
 constexpr int kOccTileMargin = 8;             // cells added around a new tile when they fit
 constexpr int kOccSmemBytes = 227 * 1024;     // tile + ring of per-ray cell lists
