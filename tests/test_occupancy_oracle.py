@@ -132,3 +132,46 @@ def test_slam_oracle_composition_tracks_the_recording(packed):
     assert all(o is not None and o[0] and o[1] < 50.0 for o in out)
     assert len(slam.map) > 1000 and np.hypot(*slam.pose[:2, 3]) > 20.0
     assert slam.occ.max() >= 0.65 and slam.occ.min() < 0.2
+
+
+def test_closed_form_bresenham_randomised():
+    """The closed form the device evaluates (floor((2 k minor + major - 1) / (2 major)) minor steps
+    after k major steps) against the reference's stepping walk on 4,000 random segments, incl.
+    axis-aligned, diagonal and single-cell ones."""
+    rng = np.random.Generator(np.random.PCG64(86112))
+    for q in range(4000):
+        span = [3, 40, 400, 3000][q % 4]
+        x0, y0, x1, y1 = (int(v) for v in rng.integers(-span, span + 1, size=4))
+        if q % 10 == 0:
+            y1 = y0
+        elif q % 10 == 1:
+            x1 = x0
+        elif q % 10 == 2:
+            x1, y1 = x0 + (y1 - y0), y1                      # exact diagonal
+        line = occ.bresenham_line(x0, y0, x1, y1)
+        assert len(line) == max(abs(x1 - x0), abs(y1 - y0)) + 1
+        ks = range(len(line)) if len(line) < 64 else list(rng.integers(0, len(line), size=48)) + [0, len(line) - 1]
+        for k in ks:
+            assert occ.bresenham_cell(x0, y0, x1, y1, int(k)) == line[int(k)], (x0, y0, x1, y1, k)
+
+
+def test_python_and_c_occupancy_oracles_agree_on_random_cases():
+    """300 seeded frames on small grids with arbitrary float32 probabilities (not only the values the
+    update itself produces), robots inside / on the border / outside, random parameters."""
+    rng = np.random.Generator(np.random.PCG64(172))
+    for q in range(300):
+        h, w = int(rng.integers(8, 48)), int(rng.integers(8, 48))
+        area = int(rng.integers(0, 30))
+        res = float(rng.choice([10.0, 30.0, 37.5]))
+        center = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+        o_p = rng.random((h, w), dtype=np.float32)
+        o_p[rng.random((h, w)) < 0.2] = np.float32(0.65)
+        i_p = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        o_c, i_c = o_p.copy(), i_p.copy()
+        robot = np.array([rng.uniform(-1.5, 1.5) * w * res, rng.uniform(-1.5, 1.5) * h * res, 0.0])
+        pts = np.zeros((int(rng.integers(0, 25)), 3))
+        pts[:, :2] = robot[:2] + rng.normal(0, (area + 2) * res, size=(len(pts), 2))
+        kw = dict(p_occ_inc=float(rng.choice([0.2, 0.35, 1.5])), p_free_dec=float(rng.choice([0.9, 0.5, 1.0])), area=area)
+        occ.update_occupancy_map(o_p, i_p, pts, robot, center, res, **kw)
+        occ.update_occupancy_map_c(o_c, i_c, pts, robot, center, res, **kw)
+        assert np.array_equal(o_p.view(np.uint32), o_c.view(np.uint32)) and np.array_equal(i_p, i_c), f"case {q}"
