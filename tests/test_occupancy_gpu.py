@@ -164,3 +164,29 @@ def test_bad_arguments_raise(pkg):
         grid.update(np.zeros((3, 2)), (0.0, 0.0), area=20000)                           # window too large
     with pytest.raises(pkg.B200IcpError):
         pkg.OccupancyGrid(50, 60, (30, 25), 30, device="cpu")
+
+
+def test_random_cases_arbitrary_probabilities(pkg):
+    """300 seeded frames on small grids with arbitrary float32 probabilities (not only the values the
+    update itself produces, a fifth of the cells exactly float32(0.65)), robots inside / on the
+    border / outside the map, windows from 0 to 29 cells, random parameters: kernel == C oracle."""
+    rng = np.random.Generator(np.random.PCG64(172))
+    for q in range(300):
+        h, w = int(rng.integers(8, 48)), int(rng.integers(8, 48))
+        area = int(rng.integers(0, 30))
+        res = float(rng.choice([10.0, 30.0, 37.5]))
+        center = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+        o = rng.random((h, w), dtype=np.float32)
+        o[rng.random((h, w)) < 0.2] = np.float32(0.65)
+        im = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        robot = np.array([rng.uniform(-1.5, 1.5) * w * res, rng.uniform(-1.5, 1.5) * h * res, 0.0])
+        pts = np.zeros((int(rng.integers(0, 25)), 3))
+        pts[:, :2] = robot[:2] + rng.normal(0, (area + 2) * res, size=(len(pts), 2))
+        kw = dict(p_occ_inc=float(rng.choice([0.2, 0.35, 1.5])), p_free_dec=float(rng.choice([0.9, 0.5, 1.0])), area=area)
+        grid = pkg.OccupancyGrid(h, w, center, res)
+        grid.probs[0].copy_(torch.from_numpy(o))
+        grid.image[0].copy_(torch.from_numpy(im))
+        grid.update(pts, robot, **kw)
+        occ.update_occupancy_map_c(o, im, pts, robot, center, res, **kw)
+        assert np.array_equal(_bits(grid.probs_numpy()), _bits(o)), f"case {q}"
+        assert np.array_equal(grid.image_numpy(), im), f"case {q}"
