@@ -20,6 +20,8 @@ FLAG_DENSE_SWEEP = 1
 FLAG_NO_SWEEP_REUSE = 2
 FLAG_WARP_KERNEL = 4
 FLAG_CTA_KERNEL = 8
+FLAG_LEGACY_WARP_KERNEL = 16
+FLAG_PAIR_WARPS_SHIFT = 8
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "CUDA", 4: "NO_DEVICE"}
 

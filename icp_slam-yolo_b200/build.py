@@ -1,21 +1,27 @@
-"""Build the CUDA library in-tree with nvcc for sm_100a (B200)."""
+"""Build the CUDA library in-tree with nvcc for sm_100a (B200).
+
+Every ``csrc/*.cu`` is compiled to an object file in ``lib/obj`` (in parallel, only when it or a
+header changed) and the objects are linked into ``lib/libb200icp.so``.
+"""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libb200icp.so")
 INCLUDE = os.path.join(REPO_ROOT, "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -23,13 +29,24 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def headers():
+    return [os.path.join(INCLUDE, "b200icp.h")] + sorted(
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+
+
+def _obj(src: str) -> str:
+    return os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(INCLUDE, "b200icp.h")]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def needs_build() -> bool:
+    return _stale(LIB_PATH, sources() + headers())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -37,13 +54,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH, *sources()]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdrs = headers()
+
+    def compile_one(src):
+        obj = _obj(src)
+        if not force and not _stale(obj, [src] + hdrs):
+            return ""
+        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        return proc.stderr
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(sources()), os.cpu_count() or 1))) as pool:
+        logs = list(pool.map(compile_one, sources()))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+        print("".join(logs))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH,
+           *[_obj(s) for s in sources()]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     return LIB_PATH

@@ -1388,6 +1388,541 @@ __global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_ke
 }
 
 // ------------------------------------------------------------------------------------
+// kernel: the whole ICP loop, W WARPS PER PAIR, two phases per iteration (icp.py:28-53)
+//
+// Round-2 throughput kernel.  What bounded icp_align_warp_kernel was latency at 16 resident warps
+// per SM (122 registers, 11.5 KB of shared memory per warp) and ~60 % of its instructions lying
+// outside the candidate sweep.  This kernel
+//   * gives a pair W warps that share ONE target tile (shared memory per warp drops by ~W/2) and is
+//     compiled for 24 resident warps per SM (<= 80 registers): the search phase and the float64
+//     phase no longer overlap in the register file --
+//       phase 1 (search): per pass of 32*SC sources -> nearest target index, stored as uint16 in
+//                shared memory; FP32 only (plus the rare float64 rescans);
+//       phase 2 (update): every source: gather of its matched target, exact float64 distance,
+//                the 11 centred sums; then warp shuffle + one shared-memory hop across the W warps,
+//                closed-form pose, apply;
+//   * extends the movement bound of the sweep reuse from "the group of 8 that holds the nearest
+//     neighbour" to the nearest neighbour itself: a pass whose sources have all moved less than half
+//     the gap between their nearest and their second-nearest target (lower bound of the in-group
+//     runner-up and of everything outside the group) skips phase 1 ENTIRELY -- no set-up, no
+//     culling, no in-group argmin -- and the iteration is gather + distance + sums only.
+// Three levels per pass, decided from the running sum of the per-iteration maximum displacement
+// (`cum_move`): cum_move <= tnn[pass]  -> indices kept;  <= tgrp[pass] -> in-group re-decision;
+// else full (pruned or dense) sweep.  Every level yields the exact float64 nearest neighbour
+// (lowest index on ties), so index histories are identical to the sweep-everything kernel.
+// ------------------------------------------------------------------------------------
+struct PairCtx {            // shared memory; touched by thread 0 only until the final barrier
+  double R[4], T[2];        // cumulative pose, src = R A + T
+  double last[4];           // last increment: cos, sin, tx, ty
+  double err, mean_d2;
+  int iters, inl;
+  unsigned long long evals; // pair evaluations executed by the sweeps of all warps
+};
+static_assert(sizeof(PairCtx) <= kCtxBytes, "PairCtx outgrew its shared-memory slot");
+
+constexpr int kPairRedStride = 12;   // doubles per warp slot of the cross-warp reduction
+
+__host__ __device__ inline size_t pair_tile_bytes(int mcap, int ncap, int passes, int warps) {
+  size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
+             (size_t)2 * warps * kPairRedStride * sizeof(double) + (size_t)passes * 2 * sizeof(float) +
+             (size_t)(mcap / kGroup) * 3 * sizeof(float) + (size_t)ncap * sizeof(unsigned short);
+  return (b + 15) & ~(size_t)15;
+}
+
+struct PairTile : WarpTile {
+  unsigned short* nnidx;    // [ncap] nearest target of every source at its last search
+  float* tgrp;              // [passes] cum_move up to which the sources of a pass keep their GROUP
+  float* tnn;               // [passes] ... keep their nearest neighbour
+  double* red;              // [2][W][kPairRedStride]
+};
+
+__device__ __forceinline__ void carve_pair_tile(unsigned char* smem, const KernelArgs& a, int warps,
+                                                PairTile& t, PairCtx*& ctx) {
+  t.mcap = a.mcap;
+  t.tile = reinterpret_cast<float*>(smem);
+  t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);
+  ctx = reinterpret_cast<PairCtx*>(t.src + a.ncap);
+  t.red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ctx) + kCtxBytes);
+  t.tgrp = reinterpret_cast<float*>(t.red + 2 * warps * kPairRedStride);
+  t.tnn = t.tgrp + a.passes;
+  t.gcx = t.tnn + a.passes;
+  t.gcy = t.gcx + a.mcap / kGroup;
+  t.grad = t.gcy + a.mcap / kGroup;
+  t.nnidx = reinterpret_cast<unsigned short*>(t.grad + a.mcap / kGroup);
+  t.grp = nullptr; t.tpass = nullptr; t.grp16 = false;
+}
+
+// CTA-cooperative version of warp_stage_targets (same tile contents for a given origin).
+template <int W>
+__device__ __forceinline__ void pair_stage_targets(PairTile& t, int tid, int lane, int warp) {
+  constexpr int NT = 32 * W;
+  double sx = 0.0, sy = 0.0;
+  for (int j = tid; j < t.m; j += NT) {
+    const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
+    sx += q.x; sy += q.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(kFull, sx, o);
+    sy += __shfl_xor_sync(kFull, sy, o);
+  }
+  if (W > 1) {
+    if (lane == 0) { t.red[warp * kPairRedStride] = sx; t.red[warp * kPairRedStride + 1] = sy; }
+    __syncthreads();
+    sx = t.red[0]; sy = t.red[1];
+#pragma unroll
+    for (int w = 1; w < W; ++w) { sx += t.red[w * kPairRedStride]; sy += t.red[w * kPairRedStride + 1]; }
+  }
+  t.ox = sx / (double)t.m;
+  t.oy = sy / (double)t.m;
+  float amax = 0.f;
+  for (int j = tid; j < t.mcap; j += NT) {
+    float cx = 1e18f, cy = 1e18f, tt = CUDART_INF_F;        // sentinels: see warp_stage_targets
+    if (j < t.m) {
+      const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
+      cx = (float)(q.x - t.ox); cy = (float)(q.y - t.oy);
+      tt = (float)((double)cx * (double)cx + (double)cy * (double)cy);
+      amax = fmaxf(amax, fmaxf(fabsf(cx), fabsf(cy)));
+    }
+    float* gq = t.tile + (j >> 3) * 24 + (j & 7);
+    gq[0] = cx; gq[8] = cy; gq[16] = tt;
+  }
+  amax = warp_max_f32(amax);
+  if (W > 1) {
+    // second buffer of the reduction scratch: the first may still be read by a slower warp
+    float* fm = reinterpret_cast<float*>(t.red + W * kPairRedStride);
+    if (lane == 0) fm[warp] = amax;
+    __syncthreads();                                         // also publishes the tile
+    amax = fm[0];
+#pragma unroll
+    for (int w = 1; w < W; ++w) amax = fmaxf(amax, fm[w]);
+  } else {
+    __syncwarp();
+  }
+  t.tmax = amax;
+  for (int g = tid; g < t.ngroups; g += NT) {                // bounding circle of every group
+    float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
+    for (int u = 0; u < kGroup; ++u) {
+      if (g * kGroup + u < t.m) {
+        const float px = t.tile[g * 24 + u], py = t.tile[g * 24 + 8 + u];
+        x0 = fminf(x0, px); x1 = fmaxf(x1, px);
+        y0 = fminf(y0, py); y1 = fmaxf(y1, py);
+      }
+    }
+    const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
+    float r2 = 0.f;
+    for (int u = 0; u < kGroup; ++u) {
+      if (g * kGroup + u < t.m) {
+        const float dx = t.tile[g * 24 + u] - cx, dy = t.tile[g * 24 + 8 + u] - cy;
+        r2 = fmaxf(r2, fmaf(dx, dx, dy * dy));
+      }
+    }
+    t.gcx[g] = cx; t.gcy[g] = cy;
+    t.grad[g] = sqrtf(r2) * 1.000004f + 1e-30f;
+  }
+}
+
+// in_group_argmin plus the two distance bounds the nearest-neighbour reuse needs: `ubd` >= the
+// exact distance from the source to the winning slot, `los` <= the exact distance to every other
+// target of the group (same FP32 error band as the near-tie guard).
+__device__ __forceinline__ int in_group_decide(const WarpTile& t, int g, float fx, float fy,
+                                               bool& near_tie, float& ubd, float& los) {
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * g;
+  const float4 xa = g4[0], xb = g4[1];
+  const float4 ya = g4[2], yb = g4[3];
+  const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy);
+  const float2 u0 = __fadd2_rn(make_float2(xa.x, xa.y), nx), v0 = __fadd2_rn(make_float2(ya.x, ya.y), ny);
+  const float2 u1 = __fadd2_rn(make_float2(xa.z, xa.w), nx), v1 = __fadd2_rn(make_float2(ya.z, ya.w), ny);
+  const float2 u2 = __fadd2_rn(make_float2(xb.x, xb.y), nx), v2 = __fadd2_rn(make_float2(yb.x, yb.y), ny);
+  const float2 u3 = __fadd2_rn(make_float2(xb.z, xb.w), nx), v3 = __fadd2_rn(make_float2(yb.z, yb.w), ny);
+  const float2 d01 = __ffma2_rn(v0, v0, __fmul2_rn(u0, u0)), d23 = __ffma2_rn(v1, v1, __fmul2_rn(u1, u1));
+  const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
+  const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
+  unsigned best = 0x7f800000u, second = 0x7f800000u;
+#pragma unroll
+  for (int u = 0; u < kGroup; ++u) {
+    const unsigned key = (__float_as_uint(ds[u]) & ~7u) | (unsigned)u;
+    second = min(second, max(best, key));
+    best = min(best, key);
+  }
+  const float bd = __uint_as_float(best & ~7u), sd = __uint_as_float(second & ~7u);
+  const float cs = fmaxf(fabsf(fx), fabsf(fy));
+  const float guard = (cs + t.tmax) * 4.76837158e-7f;                // 2^-21 (cs + tmax)
+  ubd = sqrtf(bd) * 1.000004f + guard;
+  near_tie = sd <= ubd * ubd * 1.000001f;
+  los = sqrtf(sd) * 0.999996f - guard;
+  return (int)(best & 7u);
+}
+
+// Phase 1 for one pass: the exact nearest target of the SC sources (base + k*32 + lane) of every
+// lane -> t.nnidx.  `reuse_grp`: no sweep, re-decide inside the group of the stored index.
+// bud_grp / bud_nn (identical in every lane on return): how far the sources of this pass may move
+// before one of them can leave its group / change its nearest neighbour; <= 0 means "no bound".
+template <int SC, bool PRUNE>
+__device__ __forceinline__ long long pair_search_pass(const PairTile& t, int base, int n, int m, int lane,
+                                                      bool reuse_grp, bool track, float& bud_grp,
+                                                      float& bud_nn) {
+  long long evals = 0;
+  float fx[SC], fy[SC], lbg[SC];
+#pragma unroll
+  for (int k = 0; k < SC; ++k) {
+    const double2 s = t.src[base + k * 32 + lane];
+    fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
+    lbg[k] = -1.f;
+  }
+  Candidates<SC> c;
+  if (reuse_grp) {
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      const int i = base + k * 32 + lane;
+      c.group[k] = i < n ? (int)(t.nnidx[i] >> 3) : 0;
+      c.best[k] = 0.f; c.second[k] = CUDART_INF_F;        // cross-group guard: settled by the movement bound
+    }
+  } else if (PRUNE) {
+    bool vld[SC];
+#pragma unroll
+    for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
+    float reach;
+    const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c, track ? 2.0f : 1.0f, reach);
+    evals += (long long)groups * kGroup * min(32 * SC, n - base);
+    if (track) {
+#pragma unroll
+      for (int k = 0; k < SC; ++k) lbg[k] = reach * 0.999996f;
+    }
+  } else {
+    warp_candidates<SC>(t, fx, fy, c);
+    evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
+    if (track) {
+#pragma unroll
+      for (int k = 0; k < SC; ++k) lbg[k] = CUDART_INF_F;
+    }
+  }
+  if (track && !reuse_grp) {
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      // runner-up group: d^2 >= second + |s|^2 - (FP32 error of the expanded form and of |s|^2)
+      const float cs = fmaxf(fabsf(fx[k]), fabsf(fy[k]));
+      const float ss = fmaf(fx[k], fx[k], fy[k] * fy[k]);
+      const float lo2 = (c.second[k] + ss) - (2.f * expanded_margin(cs, t.tmax) + cs * cs * 4.8e-7f);
+      lbg[k] = fminf(lbg[k], sqrtf(fmaxf(lo2, 0.f)) * 0.999996f);
+    }
+  }
+  int j[SC];
+  bool amb[SC];
+  bool any_amb = false;
+  float bg = CUDART_INF_F, bn = CUDART_INF_F;
+#pragma unroll
+  for (int k = 0; k < SC; ++k) {
+    bool tie_in;
+    float ubd, los;
+    const int slot = in_group_decide(t, c.group[k], fx[k], fy[k], tie_in, ubd, los);
+    j[k] = c.group[k] * kGroup + slot;
+    const bool valid = base + k * 32 + lane < n;
+    amb[k] = valid && (tie_in || (!reuse_grp && is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax)));
+    any_amb |= amb[k];
+    if (valid) {
+      // an ambiguous source is re-decided in float64 below: no FP32 bound describes that decision
+      bn = fminf(bn, amb[k] ? -1.f : 0.5f * (los - ubd));
+      bg = fminf(bg, amb[k] ? -1.f : 0.5f * (lbg[k] - ubd));
+    }
+  }
+  if (__any_sync(kFull, any_amb)) {      // rare: warp-cooperative float64 scan of all targets
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      unsigned pending = __ballot_sync(kFull, amb[k]);
+      if (!pending) continue;
+      const double2 s = t.src[base + k * 32 + lane];
+      int jk = j[k];
+      while (pending) {
+        const int owner = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const double qx = __shfl_sync(kFull, s.x, owner), qy = __shfl_sync(kFull, s.y, owner);
+        double ld = CUDART_INF;
+        int lj = 0x7fffffff;
+        for (int jj = lane; jj < m; jj += 32) {
+          const double d = dist2_f64(qx, qy, load_point(t.tgt, t.dtype, t.row_off + jj));
+          if (d < ld) { ld = d; lj = jj; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(kFull, ld, o);
+          const int oj = __shfl_xor_sync(kFull, lj, o);
+          if (od < ld || (od == ld && oj < lj)) { ld = od; lj = oj; }
+        }
+        if (lane == owner) jk = lj;
+      }
+      j[k] = jk;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < SC; ++k) {
+    const int i = base + k * 32 + lane;
+    if (i < n) t.nnidx[i] = (unsigned short)j[k];
+  }
+  bud_nn = warp_min_f32(bn);
+  bud_grp = (track && !reuse_grp) ? warp_min_f32(bg) : -1.f;
+  return evals;
+}
+
+#ifndef B200ICP_PAIR_RESIDENT_WARPS
+#define B200ICP_PAIR_RESIDENT_WARPS 24      // resident warps per SM the kernel is compiled for (register cap)
+#endif
+template <int SC, bool PRUNE, int W>
+__global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_align_pair_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = 32 * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t p = blockIdx.x;
+  const b200icp_problem& pr = a.prob;
+  const b200icp_options& op = a.opt;
+  const b200icp_outputs& out = a.out;
+
+  int64_t srow, trow;
+  resolve_rows(pr, p, srow, trow);
+  const int n = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
+  const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
+
+  PairTile t;
+  PairCtx* ctx;
+  carve_pair_tile(smem_raw, a, W, t, ctx);
+  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
+  t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
+
+  const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
+  if (tid == 0) {
+    double R00 = 1.0, R01 = 0.0, R10 = 0.0, R11 = 1.0, T0 = 0.0, T1 = 0.0;
+    if (op.init_pose) {
+      const double* ip = op.init_pose + p * 6;
+      R00 = ip[0]; R01 = ip[1]; R10 = ip[2]; R11 = ip[3]; T0 = ip[4]; T1 = ip[5];
+    }
+    ctx->R[0] = R00; ctx->R[1] = R01; ctx->R[2] = R10; ctx->R[3] = R11;
+    ctx->T[0] = T0; ctx->T[1] = T1;
+    ctx->last[0] = 1.0; ctx->last[1] = 0.0; ctx->last[2] = 0.0; ctx->last[3] = 0.0;
+    ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF;
+    ctx->iters = 0; ctx->inl = 0; ctx->evals = 0ull;
+  }
+  for (int q = tid; q < a.passes; q += NT) { t.tgrp[q] = -CUDART_INF_F; t.tnn[q] = -CUDART_INF_F; }
+  if (W > 1) __syncthreads(); else __syncwarp();
+  int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
+  long long evals = 0;
+
+  if (ran) {
+    pair_stage_targets<W>(t, tid, lane, warp);
+    float smax = 0.f;          // bound of |s - c| over the source points, c = target centroid
+    for (int i = tid; i < a.ncap; i += NT) {
+      double2 v = make_double2(t.ox, t.oy);                // padding slots: benign, never used
+      if (i < n) {
+        const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
+        v = q;                                             // icp.py:32  src = copy(A)
+        if (op.init_pose)
+          v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
+                           ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
+        smax = fmaxf(smax, fmaxf(__double2float_ru(fabs(v.x - t.ox)), __double2float_ru(fabs(v.y - t.oy))));
+      }
+      t.src[i] = v;
+    }
+    smax = warp_max_f32(smax);
+    if (W > 1) {
+      float* fm = reinterpret_cast<float*>(t.red);        // first buffer: free again after the staging barriers
+      if (lane == 0) fm[warp] = smax;
+      __syncthreads();                                     // also publishes src and the group circles
+      smax = fm[0];
+#pragma unroll
+      for (int w = 1; w < W; ++w) smax = fmaxf(smax, fm[w]);
+      __syncthreads();                                     // fm is reduction scratch from now on
+    } else {
+      __syncwarp();
+    }
+    smax *= 1.4142137f;
+    float mv_prev = CUDART_INF_F;      // displacement bound of the previous update
+    double prev_error = 0.0;           // icp.py:33
+    double cum_move = 0.0;             // sum of the per-iteration displacement bounds
+    const bool use_gate = a.use_gate != 0;
+    const double inv_n = 1.0 / (double)n;
+
+    for (int it = 0; it < op.max_iterations; ++it) {       // icp.py:35
+      // ---- phase 1: correspondence search (icp.py:37-38), only where the movement bound demands it
+      const bool track = a.reuse != 0 && (double)mv_prev < 0.5 * prev_error;
+      for (int pass = warp; pass < a.passes; pass += W) {
+        const int base = pass * 32 * SC;
+        if (base >= n) break;
+        const float cm = __double2float_ru(cum_move);
+        if (a.reuse != 0 && cm <= t.tnn[pass]) continue;                   // nearest neighbours provably unchanged
+        const bool reuse_grp = a.reuse != 0 && cm <= t.tgrp[pass];
+        float bud_grp, bud_nn;
+        evals += pair_search_pass<SC, PRUNE>(t, base, n, m, lane, reuse_grp, track, bud_grp, bud_nn);
+        if (a.reuse != 0 && lane == 0) {
+          if (track && !reuse_grp)
+            t.tgrp[pass] = bud_grp > 0.f ? __double2float_rd(cum_move + 0.999 * (double)bud_grp) : -CUDART_INF_F;
+          t.tnn[pass] = bud_nn > 0.f ? fminf(t.tgrp[pass], __double2float_rd(cum_move + 0.999 * (double)bud_nn))
+                                     : -CUDART_INF_F;
+        }
+      }
+      __syncwarp();
+      // ---- phase 2: gather (icp.py:39), exact distances, ONE set of centred sums
+      int32_t* hist = out.index_history
+          ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
+      double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int pass = warp; pass < a.passes; pass += W) {
+        const int base = pass * 32 * SC;
+        if (base >= n) break;
+#pragma unroll
+        for (int k0 = 0; k0 < SC; k0 += 2) {
+          int jj[2];
+          double2 bm[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {                    // both loads in flight before the first use
+            const int i = base + (k0 + u) * 32 + lane;
+            jj[u] = (k0 + u < SC && i < n) ? (int)t.nnidx[i] : 0;
+            bm[u] = load_point(t.tgt, t.dtype, t.row_off + jj[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = base + (k0 + u) * 32 + lane;
+            if (k0 + u < SC && i < n) {
+              const double2 s = t.src[i];
+              const double2 b = bm[u];
+              const double d2 = dist2_f64(s.x, s.y, b);
+              const double dist = sqrt_f64_fast(d2);
+              if (!use_gate || dist < op.max_corr_dist) {
+                const double ax = s.x - t.ox, ay = s.y - t.oy;
+                const double qx = b.x - t.ox, qy = b.y - t.oy;
+                r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
+                r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
+                r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
+                r[8] += dist; r[9] += d2; r[10] += 1.0;
+              }
+              if (idx_out) idx_out[i] = jj[u];
+              if (hist) hist[i] = jj[u];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 11; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[q] += __shfl_xor_sync(kFull, r[q], o);
+      }
+      if (W > 1) {            // one hop across the warps; every thread adds the partials in warp order
+        double* slot = t.red + ((it & 1) * W + warp) * kPairRedStride;
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < 11; ++q) slot[q] = r[q];
+        }
+        __syncthreads();
+        const double* part = t.red + (it & 1) * W * kPairRedStride;
+#pragma unroll
+        for (int q = 0; q < 11; ++q) {
+          double acc = part[q];
+#pragma unroll
+          for (int w = 1; w < W; ++w) acc += part[w * kPairRedStride + q];
+          r[q] = acc;
+        }
+      }
+      const double cnt = r[10];
+      if (cnt < 0.5) {            // every correspondence gated out: stop, search not counted
+        if (tid == 0) { ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->inl = 0; }
+        if (hist) for (int i = tid; i < n; i += NT) hist[i] = -1;
+        break;
+      }
+      const double inv = use_gate ? 1.0 / cnt : inv_n;
+      const double max_ = r[0] * inv, may_ = r[1] * inv;       // centroids rel. origin (icp.py:10-11)
+      const double mbx = r[2] * inv, mby = r[3] * inv;
+      const double mean_error = r[8] * inv;                    // icp.py:48
+      // closed-form 2D Kabsch: the proper rotation the SVD route (icp.py:17-23) returns
+      const double h00 = fma(-r[0], mbx, r[4]), h01 = fma(-r[0], mby, r[5]);
+      const double h10 = fma(-r[1], mbx, r[6]), h11 = fma(-r[1], mby, r[7]);
+      const double num = h01 - h10, den = h00 + h11;
+      const double h2 = fma(num, num, den * den);
+      double cs = 1.0, sn = 0.0;
+      if (h2 > 0.0) {
+        const double rh = rsqrt(h2);
+        cs = den * rh; sn = num * rh;
+      }
+      const double cax = t.ox + max_, cay = t.oy + may_;
+      const double tx = (t.ox + mbx) - (cs * cax - sn * cay);  // icp.py:25
+      const double ty = (t.oy + mby) - (sn * cax + cs * cay);
+      for (int pass = warp; pass < a.passes; pass += W) {      // apply (icp.py:45), own sources only
+        const int base = pass * 32 * SC;
+#pragma unroll
+        for (int k = 0; k < SC; ++k) {
+          const int i = base + k * 32 + lane;
+          if (i < n) {
+            const double2 s = t.src[i];
+            t.src[i] = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
+          }
+        }
+      }
+      // Upper bound of every point's displacement in this update: see icp_align_warp_kernel.
+      float mv = 0.f;
+      if (a.reuse) {
+        const double c1 = cs - 1.0;
+        const double rho = sqrt(fma(c1, c1, sn * sn));
+        const double ddx = fma(c1, t.ox, -sn * t.oy) + tx, ddy = fma(sn, t.ox, c1 * t.oy) + ty;
+        const double ulp = 1.0e-15 * (fabs(t.ox) + fabs(t.oy) + (double)smax + fabs(tx) + fabs(ty));
+        mv = __double2float_ru((rho * (double)smax + sqrt(fma(ddx, ddx, ddy * ddy))) * 1.000001 + ulp);
+        smax = __fadd_ru(smax, mv);
+        mv_prev = mv;
+        cum_move += (double)mv * 1.000001;
+      }
+      const bool converged = fabs(prev_error - mean_error) < op.tolerance;   // icp.py:49-50
+      prev_error = mean_error;                                               // icp.py:51
+      if (tid == 0) {            // compose the cumulative pose, record the increment
+        const double R00 = ctx->R[0], R01 = ctx->R[1], R10 = ctx->R[2], R11 = ctx->R[3];
+        const double T0 = ctx->T[0], T1 = ctx->T[1];
+        ctx->R[0] = cs * R00 - sn * R10; ctx->R[1] = cs * R01 - sn * R11;
+        ctx->R[2] = sn * R00 + cs * R10; ctx->R[3] = sn * R01 + cs * R11;
+        ctx->T[0] = cs * T0 - sn * T1 + tx; ctx->T[1] = sn * T0 + cs * T1 + ty;
+        ctx->last[0] = cs; ctx->last[1] = sn; ctx->last[2] = tx; ctx->last[3] = ty;
+        ctx->err = mean_error; ctx->mean_d2 = r[9] * inv; ctx->inl = (int)(cnt + 0.5);
+        ctx->iters = it + 1;
+      }
+      __syncwarp();
+      if (converged) break;
+    }
+  }
+
+  if (out.evaluated_pairs && lane == 0 && evals) atomicAdd(&ctx->evals, (unsigned long long)evals);
+  if (W > 1) __syncthreads(); else __syncwarp();
+  const int iters = ctx->iters;
+  if (tid == 0) {
+    double* pt = out.pose_total + p * 6;
+    pt[0] = ctx->R[0]; pt[1] = ctx->R[1]; pt[2] = ctx->R[2]; pt[3] = ctx->R[3];
+    pt[4] = ctx->T[0]; pt[5] = ctx->T[1];
+    if (out.pose_last) {
+      double* pl = out.pose_last + p * 6;
+      pl[0] = ctx->last[0]; pl[1] = -ctx->last[1]; pl[2] = ctx->last[1]; pl[3] = ctx->last[0];
+      pl[4] = ctx->last[2]; pl[5] = ctx->last[3];
+    }
+    out.error[p] = ctx->err;
+    if (out.rmse) out.rmse[p] = sqrt(ctx->mean_d2);
+    if (out.inliers) out.inliers[p] = ctx->inl;
+    out.iterations[p] = iters;
+    if (out.evaluated_pairs) out.evaluated_pairs[p] = (int64_t)ctx->evals;
+  }
+  if (idx_out) {
+    for (int i = tid; i < pr.src_pitch; i += NT)
+      if (i >= n || iters == 0) idx_out[i] = -1;
+  }
+  if (out.src_final) {
+    double2* dst = reinterpret_cast<double2*>(out.src_final) + p * pr.src_pitch;
+    for (int i = tid; i < pr.src_pitch; i += NT) {
+      double2 v = make_double2(0.0, 0.0);
+      if (i < n) {
+        if (ran) {
+          v = t.src[i];
+        } else {         // nothing ran: report the (pre-transformed) input
+          const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
+          v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
+                           ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
+        }
+      }
+      dst[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // kernel: best_fit_transform(A, B) for matched rows (icp.py:5-26), one warp per pair:
 // centroids, centred 2x2 cross-covariance (single pass relative to B's first point),
 // closed-form proper rotation, t = cB - R cA.
@@ -1789,6 +2324,48 @@ WarpShape pick_warp_shape(const b200icp_problem* prob, bool dense, const LaunchS
     }                                                                                    \
   }
 
+// W-warps-per-pair fused kernel: passes of 64 sources (pruned sweep) or 128 sources (dense sweep),
+// dealt round-robin to W <= 4 warps.  W = the warp count in 2..4 that leaves the fewest idle
+// warp-rounds, the smallest on ties: measured on B200 (profiles/r2_kernel_tuning.md) two warps beat
+// one (shared tile: 24 instead of 18 resident warps per SM) and three or four (the redundant pose
+// solve and the wait at the cross-warp sum grow with W): 360 points = 6 pruned passes on 2 warps,
+// 3 dense passes on 3.
+constexpr int kPairS = 2, kPairDenseS = 4, kPairMaxWarps = 4;
+
+int pair_warps_for(int passes, int forced) {
+  if (passes < 1) passes = 1;
+  if (forced >= 1 && forced <= kPairMaxWarps) return forced < passes ? forced : passes;
+  if (passes == 1) return 1;
+  int best = 2, best_idle = 1 << 30;
+  for (int w = 2; w <= kPairMaxWarps && w <= passes; ++w) {
+    const int idle = (passes + w - 1) / w * w - passes;
+    if (idle < best_idle) { best = w; best_idle = idle; }
+  }
+  return best;
+}
+
+int launch_pair_kernel(const b200icp_problem* prob, const LaunchShape& ls, KernelArgs& args, bool dense,
+                       int forced_warps, cudaStream_t st) {
+  const int S = dense ? kPairDenseS : kPairS;
+  args.ncap = (prob->src_pitch + 32 * S - 1) / (32 * S) * (32 * S);
+  args.passes = args.ncap / (32 * S);
+  LaunchShape ps = ls;
+  ps.warps = pair_warps_for(args.passes, forced_warps);
+  ps.smem = pair_tile_bytes(ls.mcap, args.ncap, args.passes, ps.warps);
+#define B200ICP_PAIR_CASE(W)                                                                      \
+  case W:                                                                                         \
+    return dense ? launch_pairs(icp_align_pair_kernel<kPairDenseS, false, W>, ps, args, st)       \
+                 : launch_pairs(icp_align_pair_kernel<kPairS, true, W>, ps, args, st);
+  switch (ps.warps) {
+    B200ICP_PAIR_CASE(1)
+    B200ICP_PAIR_CASE(2)
+    B200ICP_PAIR_CASE(3)
+    default:
+    B200ICP_PAIR_CASE(4)
+  }
+#undef B200ICP_PAIR_CASE
+}
+
 }  // namespace
 
 // shared with scan2map.cu (C++ linkage: not part of the C ABI)
@@ -1875,6 +2452,8 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
     cta = (n_pairs <= kAutoCtaPairs && !(opt->flags & B200ICP_FLAG_DENSE_SWEEP) && !out->evaluated_pairs) ? 1 : 0;
   if (cta == 0) {
     const bool dense = env_int("B200ICP_PRUNE", 1) == 0 || (opt->flags & B200ICP_FLAG_DENSE_SWEEP);
+    if (!(opt->flags & B200ICP_FLAG_LEGACY_WARP_KERNEL))
+      return launch_pair_kernel(prob, ls, args, dense, (opt->flags >> B200ICP_FLAG_PAIR_WARPS_SHIFT) & 7, st);
     B200ICP_DISPATCH_WARP(icp_align_warp_kernel, dense)
   }
   B200ICP_DISPATCH(icp_align_kernel)

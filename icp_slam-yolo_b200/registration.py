@@ -164,9 +164,52 @@ def _default_pairs(src, tgt, pairing, src_row, first_pair):
     return r * (r - 1) // 2 - int(first_pair)
 
 
+def _check_pairs(src, tgt, pairing, src_row, tgt_row, b, validate_rows):
+    """The C side sees pointers only: row counts are checked here."""
+    if b < 0:
+        raise ValueError("n_pairs < 0")
+    if pairing == "rowwise" and b > min(src.rows, tgt.rows):
+        raise ValueError(f"n_pairs = {b} exceeds the tables ({src.rows} source rows, {tgt.rows} target rows)")
+    if pairing == "explicit":
+        for name, t, rows in (("src_row", src_row, src.rows), ("tgt_row", tgt_row, tgt.rows)):
+            if t.dim() != 1 or t.shape[0] < b:
+                raise ValueError(f"{name} must hold at least n_pairs = {b} entries")
+            if validate_rows and b > 0:          # one device synchronisation: opt-in
+                lo, hi = int(t[:b].min()), int(t[:b].max())
+                if lo < 0 or hi >= rows:
+                    raise ValueError(f"{name} has entries outside [0, {rows})")
+
+
+def _check_out(out: "AlignResult", b: int, src_pitch: int, max_iterations: int, device) -> None:
+    """A caller-supplied result buffer is written blindly by the kernel: shapes must fit."""
+    def need(t, name, shape, dtype):
+        if t is None:
+            return
+        if t.dtype != dtype or t.device != device or not t.is_contiguous():
+            raise ValueError(f"out.{name} must be a contiguous {dtype} tensor on {device}")
+        if t.dim() != len(shape) or t.shape[0] < shape[0] or tuple(t.shape[1:]) != tuple(shape[1:]):
+            raise ValueError(f"out.{name} has shape {tuple(t.shape)}, needs [>={shape[0]}{''.join(', %d' % d for d in shape[1:])}]")
+    for name in ("pose_total", "pose_last"):
+        need(getattr(out, name), name, (b, 6), torch.float64)
+    for name in ("error", "rmse"):
+        need(getattr(out, name), name, (b,), torch.float64)
+    for name in ("inliers", "iterations"):
+        need(getattr(out, name), name, (b,), torch.int32)
+    need(out.indices, "indices", (b, src_pitch), torch.int32)
+    need(out.src_final, "src_final", (b, src_pitch, 2), torch.float64)
+    need(out.evaluated_pairs, "evaluated_pairs", (b,), torch.int64)
+    if out.index_history is not None:
+        h = out.index_history
+        if (h.dtype != torch.int32 or h.device != device or not h.is_contiguous() or h.dim() != 3 or
+                h.shape[0] < b or h.shape[1] != max_iterations or h.shape[2] != src_pitch):
+            raise ValueError(f"out.index_history must be int32 [>={b}, {max_iterations}, {src_pitch}] "
+                             f"(the kernel strides it by max_iterations), got {tuple(h.shape)}")
+
+
 def nn_search(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
               pairing: str = "rowwise", src_row=None, tgt_row=None, first_pair: int = 0,
-              want_dist2: bool = True, out_idx=None, out_dist2=None, stream=None):
+              want_dist2: bool = True, out_idx=None, out_dist2=None, validate_rows: bool = False,
+              stream=None):
     """Nearest target index for every source point of every pair.
 
     Replaces ``KDTree(B).query(src)`` (icp.py:37-38): returns (idx int32 [B,pitch],
@@ -175,6 +218,11 @@ def nn_search(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
     pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
     b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
     dev = src.points.device
+    _check_pairs(src, tgt, pairing, src_row, tgt_row, b, validate_rows)
+    for name, t, dt in (("out_idx", out_idx, torch.int32), ("out_dist2", out_dist2, torch.float64)):
+        if t is not None and (t.dtype != dt or t.device != dev or not t.is_contiguous() or t.dim() != 2 or
+                              t.shape[0] < b or t.shape[1] != src.pitch):
+            raise ValueError(f"{name} must be a contiguous {dt} [>={b}, {src.pitch}] tensor on {dev}")
     idx = out_idx if out_idx is not None else torch.empty((b, src.pitch), dtype=torch.int32, device=dev)
     d2 = out_dist2
     if d2 is None and want_dist2:
@@ -211,7 +259,8 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
                 init_pose: Optional[torch.Tensor] = None, max_corr_dist: Optional[float] = None,
                 want_indices: bool = False, want_src: bool = False, want_history: bool = False,
                 want_stats: bool = False, dense_sweep: bool = False, sweep_reuse: bool = True,
-                kernel: str = "auto", out: Optional[AlignResult] = None, stream=None) -> AlignResult:
+                kernel: str = "auto", pair_warps: int = 0, out: Optional[AlignResult] = None,
+                validate_rows: bool = False, stream=None) -> AlignResult:
     """Run the whole ICP loop of every pair on the device (one kernel launch).
 
     Replaces ``icp(A, B, max_iterations, tolerance)`` (icp.py:28-53) for a batch:
@@ -221,12 +270,16 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     provably out of reach (identical results; only worth it for spatially unordered point sets).
     ``sweep_reuse=False`` sweeps every pass in every iteration instead of skipping the sweep of a
     pass whose points provably keep their nearest neighbour's group (identical results; A/B knob).
-    ``kernel``: "auto" (CTA-per-pair fused kernel up to 2,048 pairs -- lowest latency --, warp-per-pair
-    above -- highest throughput), "warp" or "cta".
+    ``kernel``: "auto" (CTA-per-pair fused kernel up to 2,048 pairs -- lowest latency --, the
+    W-warps-per-pair throughput kernel above), "warp" (throughput kernel), "cta", or "legacy-warp"
+    (the round-1 one-warp-per-pair kernel, A/B only).  ``pair_warps`` forces W (1..4; 0 = auto).
     """
     pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
     b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
     dev = src.points.device
+    _check_pairs(src, tgt, pairing, src_row, tgt_row, b, validate_rows)
+    if out is not None:
+        _check_out(out, b, src.pitch, int(max_iterations), dev)
     if out is None:
         out = alloc_outputs(b, src.pitch, dev, max_iterations=max_iterations,
                             want_indices=want_indices, want_src=want_src, want_history=want_history,
@@ -234,7 +287,9 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     opt = _cabi.Options()
     opt.max_iterations = int(max_iterations)
     opt.flags = ((_cabi.FLAG_DENSE_SWEEP if dense_sweep else 0) | (0 if sweep_reuse else _cabi.FLAG_NO_SWEEP_REUSE) |
-                 {"auto": 0, "warp": _cabi.FLAG_WARP_KERNEL, "cta": _cabi.FLAG_CTA_KERNEL}[kernel])
+                 {"auto": 0, "warp": _cabi.FLAG_WARP_KERNEL, "cta": _cabi.FLAG_CTA_KERNEL,
+                  "legacy-warp": _cabi.FLAG_WARP_KERNEL | _cabi.FLAG_LEGACY_WARP_KERNEL}[kernel] |
+                 ((int(pair_warps) & 7) << _cabi.FLAG_PAIR_WARPS_SHIFT))
     opt.tolerance = float(tolerance)
     opt.max_corr_dist = 0.0 if max_corr_dist is None else float(max_corr_dist)
     if init_pose is not None:
@@ -262,6 +317,7 @@ def best_fit(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None, s
     (icp.py:5-26) for every pair; returns poses [B,6] (R row-major, t)."""
     pr = _problem(src, tgt, "rowwise", None, None, 0)
     b = min(src.rows, tgt.rows) if n_pairs is None else int(n_pairs)
+    _check_pairs(src, tgt, "rowwise", None, None, b, False)
     pose = torch.empty((b, 6), dtype=torch.float64, device=src.points.device)
     with torch.cuda.device(src.points.device):
         rc = _cabi.lib().b200icp_best_fit_batch(C.byref(pr), b, _ptr(pose), _stream_ptr(stream))
@@ -344,6 +400,7 @@ class HostPipeline:
         self.h_error = pin(self.n_pairs, dt=torch.float64)
         self.h_iters = pin(self.n_pairs, dt=torch.int32)
         self.launches = 0
+        self.done_event = None
 
     def bytes_per_run(self, ragged: bool):
         elt = 4 if self.dtype == torch.float32 else 8
@@ -351,12 +408,35 @@ class HostPipeline:
         d2h = self.n_pairs * (6 * 8 + 8 + 4)
         return h2d, d2h
 
+    def _check_host(self, t, name, shape, dtype):
+        if t.is_cuda or tuple(t.shape) != shape or t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous host tensor of shape {shape}, dtype {dtype}")
+        if not t.is_pinned():
+            raise ValueError(f"{name} must live in pinned host memory (tensor.pin_memory()): the copies are asynchronous")
+
     def run(self, h_src: torch.Tensor, h_tgt: torch.Tensor, h_src_len=None, h_tgt_len=None, *,
             max_iterations: int = 20, tolerance: float = 1e-5, max_corr_dist=None):
-        """h_src [B,src_pitch,2], h_tgt [B,tgt_pitch,2] pinned host tensors (row-wise pairs).
-        Returns pinned host tensors (pose_total [B,6], error [B], iterations [B]); they are
-        valid after the returned event (or a device synchronize)."""
+        """h_src [B,src_pitch,2], h_tgt [B,tgt_pitch,2] pinned host tensors (row-wise pairs);
+        h_src_len / h_tgt_len: both int32 [B] pinned host tensors, or both None (all rows full).
+        Returns pinned host tensors (pose_total [B,6], error [B], iterations [B]); they are valid
+        once ``self.done_event`` (recorded on the caller's current stream, which has been made to
+        wait for every copy of this run) has completed, or after a device synchronize.  Calls may
+        be issued back to back without synchronising: a run starts its copies only after the
+        previous run on the caller's stream has drained."""
+        if (h_src_len is None) != (h_tgt_len is None):
+            raise ValueError("pass both h_src_len and h_tgt_len, or neither")
+        self._check_host(h_src, "h_src", (self.n_pairs, self.src_pitch, 2), self.dtype)
+        self._check_host(h_tgt, "h_tgt", (self.n_pairs, self.tgt_pitch, 2), self.dtype)
+        ragged = h_src_len is not None
+        if ragged:
+            self._check_host(h_src_len, "h_src_len", (self.n_pairs,), torch.int32)
+            self._check_host(h_tgt_len, "h_tgt_len", (self.n_pairs,), torch.int32)
         main = torch.cuda.current_stream(self.device)
+        # the previous run() ended with `main` waiting for all of its copies and kernels; ordering
+        # the side streams after `main` keeps this run's first copies out of staging buffers that
+        # the previous run's kernels may still be reading
+        self.copy_stream.wait_stream(main)
+        self.out_stream.wait_stream(main)
         ready = [None, None]       # compute-done events per staging buffer
         drained = [None, None]     # results-copied events per staging buffer
         self.launches = 0
@@ -369,7 +449,7 @@ class HostPipeline:
                     self.copy_stream.wait_event(ready[ci & 1])      # kernel finished reading it
                 buf["src"][:nb].copy_(h_src[b0:b1], non_blocking=True)
                 buf["tgt"][:nb].copy_(h_tgt[b0:b1], non_blocking=True)
-                if h_src_len is not None:
+                if ragged:
                     buf["slen"][:nb].copy_(h_src_len[b0:b1], non_blocking=True)
                     buf["tlen"][:nb].copy_(h_tgt_len[b0:b1], non_blocking=True)
                 copied = torch.cuda.Event()
@@ -380,8 +460,8 @@ class HostPipeline:
             cs.wait_event(copied)
             if drained[ci & 1] is not None:
                 cs.wait_event(drained[ci & 1])                      # previous results left the buffer
-            s = ScanTable(buf["src"][:nb], buf["slen"][:nb] if h_src_len is not None else None)
-            t = ScanTable(buf["tgt"][:nb], buf["tlen"][:nb] if h_tgt_len is not None else None)
+            s = ScanTable(buf["src"][:nb], buf["slen"][:nb] if ragged else None)
+            t = ScanTable(buf["tgt"][:nb], buf["tlen"][:nb] if ragged else None)
             with torch.cuda.stream(cs):
                 align_pairs(s, t, n_pairs=nb, max_iterations=max_iterations, tolerance=tolerance,
                             max_corr_dist=max_corr_dist, kernel=self.kernel, out=buf["out"], stream=cs)
@@ -400,4 +480,8 @@ class HostPipeline:
         for ev in drained:
             if ev is not None:
                 main.wait_event(ev)
+        for cs in self.compute_streams:
+            main.wait_stream(cs)
+        self.done_event = torch.cuda.Event()
+        self.done_event.record(main)
         return self.h_pose, self.h_error, self.h_iters

@@ -38,7 +38,8 @@ extern "C" {
 #endif
 
 #define B200ICP_VERSION_MAJOR 0
-#define B200ICP_VERSION_MINOR 2   /* 0.2: occupancy-grid entry points, sweep-reuse flag */
+#define B200ICP_VERSION_MINOR 3   /* 0.3: W-warps-per-pair fused kernel; scan-to-map = exact culling +
+                                     float64 scan with the all-gather in the search epilogue */
 
 typedef enum b200icp_status {
   B200ICP_OK = 0,
@@ -103,6 +104,12 @@ typedef struct b200icp_problem {
                                        the pairs fill the GPU (> 2,048), a CTA of up to 8 warps per pair
                                        the lower latency below that (one registration per frame).
                                        Identical correspondences; poses agree to ~1e-12.          */
+
+#define B200ICP_FLAG_LEGACY_WARP_KERNEL 16 /* A/B only: the round-1 one-warp-per-pair fused kernel
+                                              instead of the W-warps-per-pair one (same results up
+                                              to the order of the float64 sums, ~1e-12)               */
+#define B200ICP_FLAG_PAIR_WARPS_SHIFT 8    /* tuning: bits 8..10 = warps per pair (1..4) of the
+                                              throughput kernel; 0 = chosen from the number of passes */
 
 typedef struct b200icp_options {
   int32_t max_iterations;   /* icp.py:28,35; reference default 20                   */
@@ -181,31 +188,51 @@ int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_
 /* ---- scan-to-map ICP: a scan of a few thousand points against a map of millions, sharded
  * contiguously across GPUs (one process per GPU).  The scan-to-local-map call shape of
  * duc/ICP_LIDAR/mainn.py:297-318 / slam_offline.py:366-392 with the point-to-point loop of
- * labels_segmentation/icp.py:28-53.  Per iteration and rank:
- *     b200icp_s2m_bound   -> ub[n]        upper bound of every point's NN distance to this shard
- *     (caller)               min-reduce of ub across ranks (32 KB)
- *     b200icp_s2m_search  -> records[n]   exact nearest map point of THIS shard per scan point
- *                                          (or "none" when the shard is out of reach of the point)
- *     (caller)               all-gather of the records of every rank  -> records_all[ranks][n]
- *     b200icp_s2m_update  -> global winner per point (distance, then lowest global index),
- *                            pose solve, apply, convergence; bit-identical on every rank.
- * Both are asynchronous and become no-ops once state->done is set, so a fixed-length loop needs
- * no host synchronisation. */
+ * labels_segmentation/icp.py:28-53 (KDTree(B).query(src), icp.py:37-38, is the search below).
+ *
+ * Once per map shard: b200icp_s2m_prepare_map -> one bounding circle per chunk of 1,024 consecutive
+ * map points and one per 32 chunks.  The circle tables of all ranks (32 bytes per 1,024 points) are
+ * gathered once by the caller and passed as b200icp_s2m_tables, so that every rank can bound a scan
+ * point's nearest-neighbour distance over the WHOLE map without a per-iteration collective.
+ * Per iteration and rank, two launches:
+ *     b200icp_s2m_search  applies the pose increment the previous update left pending; per scan
+ *                         point an upper bound of its NN distance (distance to the previous
+ *                         iteration's nearest map point; circles in the first iteration); exhaustive
+ *                         float64 scan of every local chunk whose circle is within that bound ->
+ *                         the exact nearest point of THIS shard among all that can matter (lowest
+ *                         index on ties) or "none"; the 32-byte record goes to `records`, or, with
+ *                         `peers`, straight into every rank's inbox over NVLink, followed by this
+ *                         rank's flag (the all-gather is the kernel's epilogue).
+ *     (caller)            without peers: all-gather of the records  -> records_all[ranks][n]
+ *     b200icp_s2m_update  with `inbox`: waits for the flags of all ranks (2 s timeout -> state.done
+ *                         = 2); global winner per point (distance, then lowest global index), pose
+ *                         solve, convergence; bit-identical on every rank.
+ * After the loop b200icp_s2m_finish applies the last pending increment to src64.
+ * All are asynchronous and become no-ops once state->done is set, so a fixed-length loop needs no
+ * host synchronisation (and can be captured in a CUDA graph). */
 typedef struct b200icp_s2m_shard {
   const void* points;      /* [m][2] map points of this shard (dtype below)                    */
   int64_t m;               /* points in this shard                                             */
   int64_t global_offset;   /* index of points[0] in the whole map (contiguous sharding)        */
   int32_t dtype;           /* b200icp_dtype                                                    */
   int32_t reserved;
-  /* filled by b200icp_s2m_prepare_map; caller-allocated, mcap = m rounded up to s2m_chunk(): */
-  float* cx;               /* [mcap] chunk-centred float32 x (+inf sentinels)                  */
-  float* cy;               /* [mcap]                                                           */
-  double* chunk_origin;    /* [mcap / chunk][2]                                                */
-  float* chunk_radius;     /* [mcap / chunk] max |centred coordinate|                          */
+  /* filled by b200icp_s2m_prepare_map; caller-allocated, c = b200icp_s2m_padded_chunks(m):    */
+  double* chunk_circle;    /* [c][4]: centroid x, y, bounding radius (< 0: padding), unused    */
+  double* super_circle;    /* [c / 32][4]: the same for every 32 chunks                        */
 } b200icp_s2m_shard;
 
+typedef struct b200icp_s2m_tables {   /* circles of the whole map: every rank's, in rank order */
+  const double* chunk_circle;   /* [n_chunks_total][4]                                         */
+  const double* super_circle;   /* [n_chunks_total / 32][4]                                    */
+  int32_t n_chunks_total;       /* multiple of 32                                              */
+  int32_t first_local_chunk;    /* where this rank's (padded) chunks start; multiple of 32     */
+  int32_t n_local_chunks;       /* = b200icp_s2m_padded_chunks(shard.m)                        */
+  int32_t reserved;
+} b200icp_s2m_tables;
+
 typedef struct b200icp_s2m_record {   /* 32 bytes, one per scan point and rank */
-  double d2;               /* exact float64 squared distance to the shard's nearest point      */
+  double d2;               /* exact float64 squared distance to the shard's nearest point, or
+                              +inf when no chunk of the shard can hold the nearest neighbour    */
   int64_t gidx;            /* its global map index                                             */
   double bx, by;           /* its coordinates (so no rank needs another rank's shard)          */
 } b200icp_s2m_record;
@@ -216,50 +243,47 @@ typedef struct b200icp_s2m_state {    /* device-resident, 136 bytes */
   double error;            /* mean NN distance of the last search (icp.py:48)                  */
   double mean_d2;
   double prev_error;
-  int32_t iterations, inliers, done, reserved;
+  int32_t iterations;      /* completed updates                                                */
+  int32_t inliers;
+  int32_t done;            /* 1: converged / max_iterations / all gated out; 2: a peer timed out */
+  int32_t applied;         /* increments already applied to src64 (iterations - 1 or iterations) */
 } b200icp_s2m_state;
 
 int b200icp_s2m_chunk(void);                                   /* 1024                          */
-int64_t b200icp_s2m_workspace_bytes(int32_t n_scan, int64_t m);
+int64_t b200icp_s2m_padded_chunks(int64_t m);                  /* chunks of a shard, rounded up to 32 */
+int64_t b200icp_s2m_scratch_bytes(int32_t n_scan);             /* tickets + partial sums; ZEROED once by the caller */
 int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream);
-/* src64 [n][2] float64 scan state (written), state (written) */
+/* src64 [n][2] float64 scan state (written), prev_nn [n][2] float64 (written: "none"; may be NULL
+ * for a one-shot search), state (written) */
 int b200icp_s2m_init(const void* scan, int32_t dtype, int32_t n, const double* init_pose /*[6]|NULL*/,
-                     double* src64, b200icp_s2m_state* state, void* stream);
-/* ub[n] float32: per scan point an upper bound of its NN distance to THIS shard (min over chunk
- * centres of distance + radius).  With several ranks the caller min-reduces ub across ranks
- * before the search, so that a rank sweeps only the chunks that can hold a GLOBAL winner. */
-int b200icp_s2m_bound(const b200icp_s2m_shard* shard, const double* src64, int32_t n, float* ub,
-                      const b200icp_s2m_state* state, void* stream);
-/* records[i].d2 = +inf when no chunk of this shard is within ub[i] of point i's tile. */
-int b200icp_s2m_search(const b200icp_s2m_shard* shard, const double* src64, int32_t n,
-                       const float* ub, b200icp_s2m_record* records, void* workspace,
-                       int64_t workspace_bytes, const b200icp_s2m_state* state, void* stream);
-int b200icp_s2m_update(const b200icp_s2m_record* records_all, int32_t n_ranks, double* src64,
-                       int32_t n, int32_t max_iterations, double tolerance, double max_corr_dist,
-                       int32_t* idx_out /*[n]|NULL*/, b200icp_s2m_state* state, void* stream);
+                     double* src64, double* prev_nn, b200icp_s2m_state* state, void* stream);
+/* records [n] (local output) or peers (DEVICE array of `world` inbox addresses, own inbox at
+ * [rank]); exactly one of the two is used (peers wins). */
+int b200icp_s2m_search(const b200icp_s2m_shard* shard, const b200icp_s2m_tables* tables, double* src64,
+                       const double* prev_nn /*|NULL*/, int32_t n, b200icp_s2m_record* records,
+                       void* const* peers, int32_t world, int32_t rank, b200icp_s2m_state* state,
+                       void* scratch, void* stream);
+/* records_all [n_ranks][n], or inbox (this rank's peer inbox; records_all ignored) */
+int b200icp_s2m_update(const b200icp_s2m_record* records_all, void* inbox, int32_t n_ranks,
+                       const double* src64, double* prev_nn, int32_t n, int32_t max_iterations,
+                       double tolerance, double max_corr_dist, int32_t* idx_out /*[n]|NULL*/,
+                       b200icp_s2m_state* state, void* scratch, void* stream);
+int b200icp_s2m_finish(double* src64, int32_t n, b200icp_s2m_state* state, void* scratch, void* stream);
 
 /*
- * Peer exchange for scan-to-map: the all-gather of the records done by the GPUs themselves over
- * NVLink peer stores instead of a library collective.  Every rank allocates one peer-visible
- * buffer (b200icp_peer_alloc: cudaMalloc + IPC handle; layout [2 slots][world][n] records followed
- * by [2][world] int64 flags), exchanges the 64-byte handles out of band, opens the others
- * (b200icp_peer_open) and passes the DEVICE array of the `world` buffer addresses (own buffer at
- * [rank]) to b200icp_s2m_publish, which stores this rank's records into every rank's buffer and
- * then raises this rank's flag there.  b200icp_s2m_wait blocks the stream until all flags of the
- * slot reached `seq` (2 s timeout -> state.done = 2).  Slots alternate per iteration; `seq` must
- * grow monotonically over the life of the buffer.  b200icp_s2m_update then reads
- * buffer + slot * world * n records.
+ * Peer inboxes for scan-to-map: every rank allocates one peer-visible buffer of
+ * b200icp_s2m_inbox_bytes(n, world) bytes (b200icp_peer_alloc: cudaMalloc + zero + IPC handle;
+ * layout [2 slots][world][n] records, [2][world] int64 flags, one int64 exchange counter),
+ * exchanges the 64-byte handles out of band, opens the others (b200icp_peer_open) and passes the
+ * DEVICE array of the `world` addresses to b200icp_s2m_search.  Slots alternate per exchange; the
+ * exchange counter is advanced by b200icp_s2m_update, so searches and updates must be paired and
+ * every rank must issue the same sequence of calls.
  */
+int64_t b200icp_s2m_inbox_bytes(int32_t n_scan, int32_t world);
 int b200icp_peer_alloc(int64_t bytes, void** ptr_out /*host*/, void* handle_out /*host, 64 bytes*/);
 int b200icp_peer_open(const void* handle /*host, 64 bytes*/, void** ptr_out /*host*/);
 int b200icp_peer_close(void* ptr);
 int b200icp_peer_free(void* ptr);
-int b200icp_s2m_publish(const b200icp_s2m_record* records, int32_t n, void* const* peers /*device*/,
-                        int32_t world, int32_t rank, int32_t slot, int64_t seq,
-                        void* counter /*device uint32, zeroed*/, const b200icp_s2m_state* state,
-                        void* stream);
-int b200icp_s2m_wait(const void* my_buffer, int32_t n, int32_t world, int32_t slot, int64_t seq,
-                     b200icp_s2m_state* state, void* stream);
 
 /*
  * Order-preserving selection of points (the steps either side of registration in the SLAM loop).
