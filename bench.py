@@ -52,6 +52,8 @@ def parse():
                          "configs[1], [3] and [4], reported with the same JSON shape")
     ap.add_argument("--map-points", type=int, default=1 << 24, help="scan2map: total map points")
     ap.add_argument("--scan-points", type=int, default=8192)
+    ap.add_argument("--s2m-exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--s2m-graph", action="store_true", help="scan2map: replay the 30-iteration loop as one CUDA graph")
     return ap.parse_args()
 
 
@@ -590,8 +592,8 @@ def run_scan2map(args):
     shard = m.MapShard(torch.from_numpy(full[b:e]).to(dev), global_offset=b)
     del full
     scan = torch.from_numpy(orc.synth_scan_for_map(N)).to(dev)
-    exchange = os.environ.get("B200ICP_S2M_EXCHANGE", "nccl")
-    s2m = m.ScanToMap(shard, N, exchange=exchange)
+    exchange = args.s2m_exchange
+    s2m = m.ScanToMap(shard, N, exchange=exchange, graph=args.s2m_graph)
     fp32_peak = m.ffma_probe()
 
     def step():
@@ -600,18 +602,12 @@ def run_scan2map(args):
     ms = _timed(step, args.steps, args.warmup, barrier, max_over_ranks)
     res = s2m.result()
     assert res.iterations == ITERS
-    # sweep kernel alone (the dominant kernel), CUDA events on the launching stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    st = s2m.state.clone()
-    s2m.state[16] = 0.0                                    # clear `done` so the kernels run
+    # per-kernel split of one alignment: CUDA events on the launching stream around every search / update
+    evs = []
+    s2m.run(scan, max_iterations=ITERS, tolerance=-1.0, sync=False, events=evs)
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(5):
-        s2m.search()
-    e1.record()
-    torch.cuda.synchronize()
-    search_ms = e0.elapsed_time(e1) / 5
-    s2m.state.copy_(st)
+    search_ms = sum(evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(ITERS)) / ITERS
+    update_ms = sum(evs[2 * i + 1].elapsed_time(evs[2 * i + 2]) for i in range(ITERS)) / ITERS
     if rank != 0:
         return
     evals_per_iter = float(N) * float(M)
@@ -623,19 +619,21 @@ def run_scan2map(args):
         "nn_pairs_per_s": evals_per_iter * ITERS / (ms * 1e-3),
         "config": {"workload": "configs[4]: scan-to-map ICP, %d-point scan vs %d-point map, 30 forced iterations" % (N, M),
                    "map_points_this_rank": e - b,
-                   "l2": "map shard SoA (%.0f MB) streams from L2/HBM every iteration" % ((e - b) * 8 / 1e6),
+                   "l2": "map shard %.0f MB; a scan point touches ~7 chunks of 8 KB per iteration" % ((e - b) * 8 / 1e6),
                    "parallelism": "map sharded contiguously; %s all-gather of 32 B records per iteration (%d B per rank)" % (
-                       "peer-store (NVLink, b200icp_s2m_publish/wait)" if exchange == "peer" else "NCCL", N * 32),
+                       "peer stores over NVLink in the search epilogue + flags" if (exchange == "peer" and world > 1) else ("NCCL" if world > 1 else "single rank: none"), N * 32),
+                   "cuda_graph": bool(args.s2m_graph),
                    "final_error_mm": res.error},
         "gpu_launches": args.steps * s2m.launches,
-        "roofline": {"bound": "fp32", "kernel": "s2m_sweep_kernel (+ resolve/exact)",
-                     "achieved": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12, "peak": fp32_peak,
-                     "unit": "TFLOP/s", "frac": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12 / fp32_peak,
-                     "kernel_ms": search_ms, "traffic": None,
+        "per_iteration_ms": {"search": search_ms, "update_incl_peer_wait": update_ms},
+        "roofline": {"bound": "fp64", "kernel": "s2m_search_kernel",
+                     "achieved": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12, "peak": None,
+                     "unit": "TFLOP/s (brute-force-equivalent)", "frac": None,
+                     "kernel_ms": search_ms, "traffic": None, "ffma_peak_tflops": fp32_peak,
                      "note": "achieved = brute-force-equivalent work (N_scan x M_shard x 5 FLOP per search) / time of "
-                             "one b200icp_s2m_search (bound + cull + sweep + resolve + exact kernels).  Chunks that are "
-                             "provably out of reach of a 512-point tile are culled (identical results), so frac can "
-                             "exceed 1: it is not an FP32-pipe utilisation."},
+                             "one b200icp_s2m_search.  Chunks of 1,024 map points whose bounding circle is provably "
+                             "farther than a point's nearest neighbour are skipped and the rest are scanned in float64 "
+                             "(identical results), so this is not a pipe utilisation: no frac is claimed."},
     }
     print(json.dumps(line), flush=True)
 

@@ -58,8 +58,15 @@ class S2MShard(C.Structure):
     _fields_ = [
         ("points", C.c_void_p), ("m", C.c_int64), ("global_offset", C.c_int64),
         ("dtype", C.c_int32), ("reserved", C.c_int32),
-        ("cx", C.c_void_p), ("cy", C.c_void_p), ("chunk_origin", C.c_void_p),
-        ("chunk_radius", C.c_void_p),
+        ("chunk_circle", C.c_void_p), ("super_circle", C.c_void_p),
+    ]
+
+
+class S2MTables(C.Structure):
+    _fields_ = [
+        ("chunk_circle", C.c_void_p), ("super_circle", C.c_void_p),
+        ("n_chunks_total", C.c_int32), ("first_local_chunk", C.c_int32),
+        ("n_local_chunks", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -97,23 +104,23 @@ SYMBOLS = {
                                             C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                             C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200icp_s2m_chunk": (C.c_int, []),
-    "b200icp_s2m_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
+    "b200icp_s2m_padded_chunks": (C.c_int64, [C.c_int64]),
+    "b200icp_s2m_scratch_bytes": (C.c_int64, [C.c_int32]),
+    "b200icp_s2m_inbox_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p]),
     "b200icp_s2m_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p]),
-    "b200icp_s2m_bound": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                    C.c_void_p]),
-    "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.POINTER(S2MTables), C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "b200icp_s2m_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "b200icp_s2m_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200icp_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "b200icp_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200icp_peer_close": (C.c_int, [C.c_void_p]),
     "b200icp_peer_free": (C.c_int, [C.c_void_p]),
-    "b200icp_s2m_publish": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b200icp_s2m_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
-    "b200icp_s2m_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                     C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -235,6 +235,53 @@ struct SearchArgs {
   unsigned* scratch;
 };
 
+// Is the circle within `reach` of the point?  (squared, rounded so that a true hit is never lost)
+__device__ __forceinline__ bool circle_hit(const Circle& c, double sx, double sy, double ub) {
+  if (!(c.r >= 0.0)) return false;
+  const double dx = sx - c.ox, dy = sy - c.oy, reach = ub + c.r;
+  return (dx * dx + dy * dy) * kDown <= reach * reach;
+}
+
+// Exhaustive float64 scan of one chunk for one point: lanes stride over the chunk, eight
+// independent loads in flight per lane, strict < in ascending index per lane.
+__device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double sx, double sy, int lane,
+                                           double& bd, long long& bj) {
+  const int64_t j0 = (int64_t)lc * kChunk;
+  const int cnt = (int)min((int64_t)kChunk, a.m - j0);
+  int j = lane;
+  if (a.dtype == B200ICP_F32) {
+    const float2* __restrict__ p = reinterpret_cast<const float2*>(a.points) + j0;
+    for (; j + 224 < cnt; j += 256) {
+      float2 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = __ldg(p + j + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double d = dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y));
+        if (d < bd) { bd = d; bj = j0 + j + 32 * u; }
+      }
+    }
+  } else {
+    const double2* __restrict__ p = reinterpret_cast<const double2*>(a.points) + j0;
+    for (; j + 96 < cnt; j += 128) {
+      double2 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(p + j + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double d = dist2_f64(sx, sy, q[u]);
+        if (d < bd) { bd = d; bj = j0 + j + 32 * u; }
+      }
+    }
+  }
+  for (; j < cnt; j += 32) {
+    const double d = dist2_f64(sx, sy, load_point(a.points, a.dtype, j0 + j));
+    if (d < bd) { bd = d; bj = j0 + j; }
+  }
+}
+
+constexpr int kSuperBlock = 1024;     // super-chunks per traversal block: one candidate bit per lane and trip
+
 __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const SearchArgs a) {
   b200icp_s2m_state* st = a.state;
   if (st->done) return;
@@ -254,31 +301,24 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
       if (lane == 0) { a.src64[2 * i] = s.x; a.src64[2 * i + 1] = s.y; }
     }
     // ---- (2) upper bound of the nearest-neighbour distance over the whole map
-    double ub2;                                   // squared, rounded up
+    double ub;
     const double px = a.prev_nn ? a.prev_nn[2 * i] : CUDART_NAN, py = a.prev_nn ? a.prev_nn[2 * i + 1] : CUDART_NAN;
     if (px == px) {
-      ub2 = dist2_f64(s.x, s.y, make_double2(px, py)) * kUp;
+      ub = sqrt(dist2_f64(s.x, s.y, make_double2(px, py)) * kUp) * kUp;
     } else {
       const int n_super = a.n_chunks_total / kSuper;
-      double ub = CUDART_INF;
+      double ub0 = CUDART_INF;
       for (int k = lane; k < n_super; k += 32) {
         const Circle c = load_circle(a.super_circle, k);
         if (c.r >= 0.0) {
           const double dx = s.x - c.ox, dy = s.y - c.oy;
-          ub = fmin(ub, sqrt(dx * dx + dy * dy) * kUp + c.r);
+          ub0 = fmin(ub0, sqrt(dx * dx + dy * dy) * kUp + c.r);
         }
       }
-      ub = warp_min_f64(ub);
-      double ub1 = ub;
+      ub0 = warp_min_f64(ub0);
+      double ub1 = ub0;
       for (int k0 = 0; k0 < n_super; k0 += 32) {
-        bool near = false;
-        if (k0 + lane < n_super) {
-          const Circle c = load_circle(a.super_circle, k0 + lane);
-          if (c.r >= 0.0) {
-            const double dx = s.x - c.ox, dy = s.y - c.oy, reach = ub + c.r;
-            near = (dx * dx + dy * dy) * kDown <= reach * reach;
-          }
-        }
+        const bool near = k0 + lane < n_super && circle_hit(load_circle(a.super_circle, k0 + lane), s.x, s.y, ub0);
         unsigned mask = __ballot_sync(kFull, near);
         while (mask) {
           const int k = k0 + __ffs(mask) - 1;
@@ -291,53 +331,62 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
         }
       }
       ub = warp_min_f64(ub1) * kUp;
-      ub2 = ub * ub * kUp;
     }
-    // ---- (3) exact float64 scan of every local chunk within reach
+    // ---- (3) exact float64 scan of every local chunk within reach.  Two traversals of the local
+    // circles: the first finds the chunk whose centre is closest; if the bound is wider than that
+    // chunk (the scan moved a lot, or this is the first iteration) the chunk is scanned first and
+    // its best distance becomes the bound.  The second scans every chunk within the bound.
     double bd = CUDART_INF;
     long long bj = kNoIndex;
     const int first_super = a.first_local_chunk / kSuper, local_supers = a.n_local_chunks / kSuper;
-    const double ub = sqrt(ub2) * kUp;
-    for (int k0 = 0; k0 < local_supers; k0 += 32) {
-      bool near = false;
-      if (k0 + lane < local_supers) {
-        const Circle c = load_circle(a.super_circle, first_super + k0 + lane);
-        if (c.r >= 0.0) {
-          const double dx = s.x - c.ox, dy = s.y - c.oy, reach = ub + c.r;
-          near = (dx * dx + dy * dy) * kDown <= reach * reach;
+    for (int phase = 0; phase < 2; ++phase) {
+      double cd = CUDART_INF, cr = 0.0;       // closest chunk centre among the candidates (phase 0)
+      int cc = -1;
+      for (int b0 = 0; b0 < local_supers; b0 += kSuperBlock) {
+        const int trips = (min(kSuperBlock, local_supers - b0) + 31) >> 5;
+        unsigned my = 0;                      // bit t: super b0 + 32 t + lane is within reach (loads independent)
+        for (int t = 0; t < trips; ++t) {
+          const int k = b0 + 32 * t + lane;
+          const bool near = k < local_supers && circle_hit(load_circle(a.super_circle, first_super + k), s.x, s.y, ub);
+          my |= (near ? 1u : 0u) << t;
+        }
+        if (!__any_sync(kFull, my != 0)) continue;
+        for (int t = 0; t < trips; ++t) {
+          unsigned smask = __ballot_sync(kFull, (my >> t) & 1u);
+          while (smask) {
+            const int ks = b0 + 32 * t + __ffs(smask) - 1;             // local super-chunk
+            smask &= smask - 1;
+            const Circle c = load_circle(a.chunk_circle, (int64_t)(first_super + ks) * kSuper + lane);
+            const bool hit = circle_hit(c, s.x, s.y, ub);
+            if (phase == 0) {
+              if (hit) {
+                const double dx = s.x - c.ox, dy = s.y - c.oy, d = dx * dx + dy * dy;
+                if (d < cd) { cd = d; cr = c.r; cc = ks * kSuper + lane; }
+              }
+            } else {
+              unsigned cmask = __ballot_sync(kFull, hit);
+              while (cmask) {
+                const int lc = ks * kSuper + __ffs(cmask) - 1;           // local chunk, ascending
+                cmask &= cmask - 1;
+                scan_chunk(a, lc, s.x, s.y, lane, bd, bj);
+              }
+            }
+          }
         }
       }
-      unsigned smask = __ballot_sync(kFull, near);
-      while (smask) {
-        const int ks = k0 + __ffs(smask) - 1;               // local super-chunk index
-        smask &= smask - 1;
-        const Circle c = load_circle(a.chunk_circle, (int64_t)(first_super + ks) * kSuper + lane);
-        bool hit = false;
-        if (c.r >= 0.0) {
-          const double dx = s.x - c.ox, dy = s.y - c.oy, reach = ub + c.r;
-          hit = (dx * dx + dy * dy) * kDown <= reach * reach;
+      if (phase == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(kFull, cd, o), orr = __shfl_xor_sync(kFull, cr, o);
+          const int oc = __shfl_xor_sync(kFull, cc, o);
+          if (od < cd || (od == cd && oc >= 0 && (cc < 0 || oc < cc))) { cd = od; cr = orr; cc = oc; }
         }
-        unsigned cmask = __ballot_sync(kFull, hit);
-        while (cmask) {
-          const int lc = ks * kSuper + __ffs(cmask) - 1;     // local chunk index
-          cmask &= cmask - 1;
-          const int64_t j0 = (int64_t)lc * kChunk;
-          const int cnt = (int)min((int64_t)kChunk, a.m - j0);
-          int j = lane;
-          for (; j + 96 < cnt; j += 128) {                   // four loads in flight; ascending j per lane
-            const double2 q0 = load_point(a.points, a.dtype, j0 + j), q1 = load_point(a.points, a.dtype, j0 + j + 32);
-            const double2 q2 = load_point(a.points, a.dtype, j0 + j + 64), q3 = load_point(a.points, a.dtype, j0 + j + 96);
-            const double d0 = dist2_f64(s.x, s.y, q0), d1 = dist2_f64(s.x, s.y, q1);
-            const double d2 = dist2_f64(s.x, s.y, q2), d3 = dist2_f64(s.x, s.y, q3);
-            if (d0 < bd) { bd = d0; bj = j0 + j; }
-            if (d1 < bd) { bd = d1; bj = j0 + j + 32; }
-            if (d2 < bd) { bd = d2; bj = j0 + j + 64; }
-            if (d3 < bd) { bd = d3; bj = j0 + j + 96; }
-          }
-          for (; j < cnt; j += 32) {
-            const double d = dist2_f64(s.x, s.y, load_point(a.points, a.dtype, j0 + j));
-            if (d < bd) { bd = d; bj = j0 + j; }
-          }
+        if (cc >= 0 && ub > cr) {             // the bound is wider than the closest chunk: tighten it there
+          double td = CUDART_INF;
+          long long tj = kNoIndex;
+          scan_chunk(a, cc, s.x, s.y, lane, td, tj);
+          td = warp_min_f64(td);
+          ub = fmin(ub, sqrt(td * kUp) * kUp);
         }
       }
     }

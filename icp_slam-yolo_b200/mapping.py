@@ -53,9 +53,7 @@ def remove_dynamic_points(current_points: torch.Tensor, prev_points: Optional[to
     else:                       # large sets: one search of the sharded-map path
         from .scan_to_map import MapShard, ScanToMap
         s2m = ScanToMap(MapShard(prev_points.contiguous()), n, local_only=True)
-        rc = lib.b200icp_s2m_init(_ptr(current_points), _DTYPES[current_points.dtype], n, None,
-                                  _ptr(s2m.src64), _ptr(s2m.state), _stream_ptr(None))
-        _cabi.check(rc, "b200icp_s2m_init")
+        s2m.init(current_points.contiguous())
         s2m.search()
         key = s2m.records[:, 0].contiguous()
     return _select(current_points, 0, key, 0.0, 0.0, float(distance_threshold) ** 2)

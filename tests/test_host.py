@@ -29,7 +29,7 @@ def test_cabi_exports_every_declared_symbol(pkg):
         assert hasattr(handle, name), f"{name} declared in b200icp.h but not exported"
     from icp_slam_yolo_b200 import _cabi
     assert set(_cabi.SYMBOLS) == declared
-    assert pkg.lib().b200icp_version() == 2
+    assert pkg.lib().b200icp_version() == 3
     assert pkg.lib().b200icp_max_src_pitch() == 1024 and pkg.lib().b200icp_max_tgt_pitch() == 4096
 
 
