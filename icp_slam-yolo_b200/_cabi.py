@@ -20,7 +20,6 @@ FLAG_DENSE_SWEEP = 1
 FLAG_NO_SWEEP_REUSE = 2
 FLAG_WARP_KERNEL = 4
 FLAG_CTA_KERNEL = 8
-FLAG_LEGACY_WARP_KERNEL = 16
 FLAG_PAIR_WARPS_SHIFT = 8
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "CUDA", 4: "NO_DEVICE"}
@@ -51,6 +50,13 @@ class Outputs(C.Structure):
         ("rmse", C.c_void_p), ("inliers", C.c_void_p), ("iterations", C.c_void_p),
         ("indices", C.c_void_p), ("src_final", C.c_void_p), ("index_history", C.c_void_p),
         ("evaluated_pairs", C.c_void_p),
+    ]
+
+
+class PolarFilter(C.Structure):
+    _fields_ = [
+        ("min_dist", C.c_double), ("max_dist", C.c_double), ("min_quality", C.c_double),
+        ("arc_lo", C.c_double), ("arc_hi", C.c_double), ("use_arc", C.c_int32), ("y_sign", C.c_int32),
     ]
 
 
@@ -85,11 +91,11 @@ SYMBOLS = {
     "b200icp_last_error": (C.c_char_p, []),
     "b200icp_max_src_pitch": (C.c_int, []),
     "b200icp_max_tgt_pitch": (C.c_int, []),
-    "b200icp_nn_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200icp_nn_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200icp_align_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.POINTER(Options),
                                       C.POINTER(Outputs), C.c_void_p]),
     "b200icp_best_fit_batch": (C.c_int, [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p]),
-    "b200icp_polar_to_cartesian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+    "b200icp_polar_to_cartesian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200icp_ffma_probe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_void_p]),
     "b200icp_select_points": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_double,

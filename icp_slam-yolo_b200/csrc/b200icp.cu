@@ -47,14 +47,6 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef B200ICP_MIN_BLOCKS
 #define B200ICP_MIN_BLOCKS 2
 #endif
-// resident one-warp CTAs per SM the warp-per-pair kernel is compiled for (register cap
-// 65536 / (32 * this), rounded down to the allocation granule)
-#ifndef B200ICP_WARP_MIN_BLOCKS
-#define B200ICP_WARP_MIN_BLOCKS 16
-#endif
-#ifndef B200ICP_EVAL_UNROLL2
-#define B200ICP_EVAL_UNROLL2 0
-#endif
 
 thread_local char g_last_error[512] = "";
 
@@ -168,7 +160,6 @@ __device__ __forceinline__ void carve_tile(unsigned char* smem, int mcap, Target
 }
 
 // Stage the target scan: float64 copy, centroid, centred float32 SoA copies (+ |t|^2), pad.
-template <bool EXPANDED>
 __device__ __forceinline__ void stage_targets(const void* tgt, int dtype, int64_t row_off, int m,
                                               TargetTile& t, int tid, int nthreads, int warp,
                                               int lane, int nwarps) {
@@ -192,16 +183,10 @@ __device__ __forceinline__ void stage_targets(const void* tgt, int dtype, int64_
       const double2 q = t.t64[j];
       const float cx = (float)(q.x - t.ox), cy = (float)(q.y - t.oy);
       amax = fmaxf(amax, fmaxf(fabsf(cx), fabsf(cy)));
-      if (EXPANDED) {
-        t.fx[j] = cx; t.fy[j] = cy;
-        t.ft[j] = (float)((double)cx * (double)cx + (double)cy * (double)cy);
-      } else {
-        t.fx[j] = -cx; t.fy[j] = -cy;
-      }
-    } else if (EXPANDED) {
-      t.fx[j] = 0.f; t.fy[j] = 0.f; t.ft[j] = CUDART_INF_F;
+      t.fx[j] = cx; t.fy[j] = cy;
+      t.ft[j] = (float)((double)cx * (double)cx + (double)cy * (double)cy);
     } else {
-      t.fx[j] = CUDART_INF_F; t.fy[j] = CUDART_INF_F;
+      t.fx[j] = 0.f; t.fy[j] = 0.f; t.ft[j] = CUDART_INF_F;
     }
   }
 #pragma unroll
@@ -236,7 +221,7 @@ __device__ __forceinline__ void track(Candidates<S>& c, int k, float m, int g) {
   c.best[k] = fminf(old, m);
 }
 
-template <int S, bool EXPANDED>
+template <int S>
 __device__ __forceinline__ void nn_candidates(const TargetTile& t, const float (&sx)[S],
                                               const float (&sy)[S], Candidates<S>& c) {
   const float4* __restrict__ x4 = reinterpret_cast<const float4*>(t.fx);
@@ -245,8 +230,8 @@ __device__ __forceinline__ void nn_candidates(const TargetTile& t, const float (
   float a[S], b[S];
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    float vx = EXPANDED ? -2.0f * sx[k] : sx[k];
-    float vy = EXPANDED ? -2.0f * sy[k] : sy[k];
+    float vx = -2.0f * sx[k];
+    float vy = -2.0f * sy[k];
     // opaque copies: stops ptxas from re-converting the float64 state inside the loop
     asm volatile("" : "+f"(vx), "+f"(vy));
     a[k] = vx; b[k] = vy;
@@ -259,35 +244,19 @@ __device__ __forceinline__ void nn_candidates(const TargetTile& t, const float (
   for (int g = 0; g < ngroups; ++g) {
     const float4 xa = x4[2 * g], xb = x4[2 * g + 1];
     const float4 ya = y4[2 * g], yb = y4[2 * g + 1];
-    if (EXPANDED) {
-      const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
+    const float4 qa = q4[2 * g], qb = q4[2 * g + 1];
 #pragma unroll
-      for (int k = 0; k < S; ++k) {
-        // packed FP32x2: two targets per FFMA2 issue slot (the loop is issue/ALU bound,
-        // not FMA-pipe bound: profiles/r1_ubench_issue_rates.txt)
-        const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
-        const float2 e01 = __ffma2_rn(ak, make_float2(xa.x, xa.y), __ffma2_rn(bk, make_float2(ya.x, ya.y), make_float2(qa.x, qa.y)));
-        const float2 e23 = __ffma2_rn(ak, make_float2(xa.z, xa.w), __ffma2_rn(bk, make_float2(ya.z, ya.w), make_float2(qa.z, qa.w)));
-        const float2 e45 = __ffma2_rn(ak, make_float2(xb.x, xb.y), __ffma2_rn(bk, make_float2(yb.x, yb.y), make_float2(qb.x, qb.y)));
-        const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
-        const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
-                              fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
-        track<S>(c, k, m, g);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const float u0 = a[k] + xa.x, v0 = b[k] + ya.x, u1 = a[k] + xa.y, v1 = b[k] + ya.y;
-        const float u2 = a[k] + xa.z, v2 = b[k] + ya.z, u3 = a[k] + xa.w, v3 = b[k] + ya.w;
-        const float u4 = a[k] + xb.x, v4 = b[k] + yb.x, u5 = a[k] + xb.y, v5 = b[k] + yb.y;
-        const float u6 = a[k] + xb.z, v6 = b[k] + yb.z, u7 = a[k] + xb.w, v7 = b[k] + yb.w;
-        const float d0 = fmaf(v0, v0, u0 * u0), d1 = fmaf(v1, v1, u1 * u1);
-        const float d2 = fmaf(v2, v2, u2 * u2), d3 = fmaf(v3, v3, u3 * u3);
-        const float d4 = fmaf(v4, v4, u4 * u4), d5 = fmaf(v5, v5, u5 * u5);
-        const float d6 = fmaf(v6, v6, u6 * u6), d7 = fmaf(v7, v7, u7 * u7);
-        const float m = fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(fminf(d4, d5), fminf(d6, d7)));
-        track<S>(c, k, m, g);
-      }
+    for (int k = 0; k < S; ++k) {
+      // packed FP32x2: two targets per FFMA2 issue slot (the loop is issue/ALU bound,
+      // not FMA-pipe bound: profiles/r1_ubench_issue_rates.txt)
+      const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
+      const float2 e01 = __ffma2_rn(ak, make_float2(xa.x, xa.y), __ffma2_rn(bk, make_float2(ya.x, ya.y), make_float2(qa.x, qa.y)));
+      const float2 e23 = __ffma2_rn(ak, make_float2(xa.z, xa.w), __ffma2_rn(bk, make_float2(ya.z, ya.w), make_float2(qa.z, qa.w)));
+      const float2 e45 = __ffma2_rn(ak, make_float2(xb.x, xb.y), __ffma2_rn(bk, make_float2(yb.x, yb.y), make_float2(qb.x, qb.y)));
+      const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
+      const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
+                            fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
+      track<S>(c, k, m, g);
     }
   }
 }
@@ -315,14 +284,9 @@ __device__ __forceinline__ float expanded_margin(float cs, float tmax) {
   return 9.5367432e-7f * (cs + tmax) * fmaf(1.2f, fmaxf(cs, tmax), tmax);
 }
 
-template <bool EXPANDED>
-__device__ __forceinline__ bool is_ambiguous(float best, float second, float scx, float scy,
-                                             float tmax) {
+__device__ __forceinline__ bool is_ambiguous(float best, float second, float scx, float scy, float tmax) {
   const float cs = fmaxf(fabsf(scx), fabsf(scy));
-  if (EXPANDED) return (second - best) <= expanded_margin(cs, tmax);   // near-equal floats subtract exactly
-  const float guard = (cs + tmax) * 4.76837158e-7f;                         // 4*eta = 2^-21 (..)
-  const float r = sqrtf(best) * 1.00000095f + guard;
-  return second <= r * r * 1.00000024f;
+  return (second - best) <= expanded_margin(cs, tmax);   // near-equal floats subtract exactly
 }
 
 // sqrt of a float64 in [~1e-30, ~1e30]: FP32 rsqrt seed + two Newton steps on the residual
@@ -340,7 +304,7 @@ __device__ __forceinline__ double sqrt_f64_fast(double x) {
 }
 
 // Re-decide every correspondence in float64.  Must be called by all lanes of the warp.
-template <int S, bool EXPANDED>
+template <int S>
 __device__ __forceinline__ void nn_resolve(const TargetTile& t, const Candidates<S>& c,
                                            const double (&sx)[S], const double (&sy)[S],
                                            const float (&fx)[S], const float (&fy)[S],
@@ -349,7 +313,7 @@ __device__ __forceinline__ void nn_resolve(const TargetTile& t, const Candidates
   const double2* __restrict__ t64 = t.t64;
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    const bool ambiguous = valid[k] && is_ambiguous<EXPANDED>(c.best[k], c.second[k], fx[k], fy[k], t.tmax);
+    const bool ambiguous = valid[k] && is_ambiguous(c.best[k], c.second[k], fx[k], fy[k], t.tmax);
     // fast path: the winner is inside the best group; rescan its 8 targets exactly
     // (ascending index, strict <: lowest index wins exact ties)
     double bd = CUDART_INF;
@@ -389,7 +353,7 @@ __device__ __forceinline__ void nn_resolve(const TargetTile& t, const Candidates
 }
 
 // One full search for the S source points a lane owns (float64 in, exact answer out).
-template <int S, bool EXPANDED>
+template <int S>
 __device__ __forceinline__ void nn_search(const TargetTile& t, const double (&sx)[S],
                                           const double (&sy)[S], const bool (&valid)[S], int lane,
                                           int (&idx)[S], double (&d2)[S]) {
@@ -400,14 +364,14 @@ __device__ __forceinline__ void nn_search(const TargetTile& t, const double (&sx
     fy[k] = (float)(sy[k] - t.oy);
   }
   Candidates<S> c;
-  nn_candidates<S, EXPANDED>(t, fx, fy, c);
-  nn_resolve<S, EXPANDED>(t, c, sx, sy, fx, fy, valid, lane, idx, d2);
+  nn_candidates<S>(t, fx, fy, c);
+  nn_resolve<S>(t, c, sx, sy, fx, fy, valid, lane, idx, d2);
 }
 
 // ------------------------------------------------------------------------------------
 // kernel: nearest-neighbour search only (icp.py:37-38)
 // ------------------------------------------------------------------------------------
-template <int S, bool EXPANDED>
+template <int S>
 __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) nn_pair_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TargetTile t;
@@ -432,7 +396,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) nn_pair_ke
     }
     return;
   }
-  stage_targets<EXPANDED>(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, t, tid, nthreads, warp,
+  stage_targets(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, t, tid, nthreads, warp,
                           lane, nwarps);
   double sx[S], sy[S];
   bool valid[S];
@@ -446,7 +410,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) nn_pair_ke
   }
   int idx[S];
   double d2[S];
-  nn_search<S, EXPANDED>(t, sx, sy, valid, lane, idx, d2);
+  nn_search<S>(t, sx, sy, valid, lane, idx, d2);
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     const int i = tid + k * nthreads;
@@ -460,7 +424,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) nn_pair_ke
 // ------------------------------------------------------------------------------------
 // kernel: the whole ICP loop for one pair (icp.py:28-53)
 // ------------------------------------------------------------------------------------
-template <int S, bool EXPANDED>
+template <int S>
 __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) icp_align_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TargetTile t;
@@ -497,7 +461,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) icp_align_
 
   const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
   if (ran) {
-    stage_targets<EXPANDED>(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, t, tid, nthreads,
+    stage_targets(pr.tgt_points, pr.dtype, trow * pr.tgt_pitch, m, t, tid, nthreads,
                             warp, lane, nwarps);
 #pragma unroll
     for (int k = 0; k < S; ++k) {
@@ -521,7 +485,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, B200ICP_MIN_BLOCKS) icp_align_
     for (int it = 0; it < op.max_iterations; ++it) {           // icp.py:35
       // ---- correspondence search (icp.py:37-38)
       double d2[S];
-      nn_search<S, EXPANDED>(t, sx, sy, valid, lane, idx, d2);
+      nn_search<S>(t, sx, sy, valid, lane, idx, d2);
       // ---- gather matches (icp.py:39), gate, ONE reduction of centred sums.
       // Coordinates are taken relative to the tile origin (the target centroid), so the
       // single-pass covariance  H = sum a'b'^T - (sum a')(sum b')^T / n  (icp.py:10-16) loses
@@ -668,73 +632,7 @@ struct WarpTile {
   int m, mcap, ngroups;
 };
 
-// Shared memory of one warp-per-pair CTA.  Every byte counts: at 360 x 360 points 16 CTAs per SM
-// need <= 11,520 B each to stay inside the 196 KB carve-out, which leaves the L1 that the
-// matched-target gathers hit; one more 16-byte granule and the SM falls back to 28 KB of L1.
-constexpr int kCtxBytes = 128;        // WarpCtx
-__host__ __device__ inline size_t warp_tile_bytes(int mcap, int ncap, int src_pitch, int passes, bool reuse) {
-  size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
-             (size_t)passes * sizeof(float) + (size_t)(mcap / kGroup) * 3 * sizeof(float);
-  if (reuse) b += (size_t)src_pitch * (mcap / kGroup > 256 ? 2 : 1);      // grp: the fused loop only
-  return (b + 15) & ~(size_t)15;
-}
-
-__device__ __forceinline__ void warp_stage_targets(WarpTile& t, int lane) {
-  double sx = 0.0, sy = 0.0;
-  for (int j = lane; j < t.m; j += 32) {
-    const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
-    sx += q.x; sy += q.y;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sx += __shfl_xor_sync(kFull, sx, o);
-    sy += __shfl_xor_sync(kFull, sy, o);
-  }
-  t.ox = sx / (double)t.m;
-  t.oy = sy / (double)t.m;
-  float amax = 0.f;
-  for (int j = lane; j < t.mcap; j += 32) {
-    // sentinels: |t|^2 = +inf makes the expanded form +inf (no inf - inf: the coordinates stay
-    // finite), and 1e18 makes the direct-difference form ~2e36, finite and never the minimum
-    float cx = 1e18f, cy = 1e18f, tt = CUDART_INF_F;
-    if (j < t.m) {
-      const double2 q = load_point(t.tgt, t.dtype, t.row_off + j);
-      cx = (float)(q.x - t.ox); cy = (float)(q.y - t.oy);
-      tt = (float)((double)cx * (double)cx + (double)cy * (double)cy);
-      amax = fmaxf(amax, fmaxf(fabsf(cx), fabsf(cy)));
-    }
-    float* gq = t.tile + (j >> 3) * 24 + (j & 7);
-    gq[0] = cx; gq[8] = cy; gq[16] = tt;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFull, amax, o));
-  t.tmax = amax;
-  __syncwarp();
-  // bounding circle of every group (valid targets only), radius rounded up
-  for (int g = lane; g < t.ngroups; g += 32) {
-    float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
-    for (int u = 0; u < kGroup; ++u) {
-      const int j = g * kGroup + u;
-      if (j < t.m) {
-        const float px = t.tile[g * 24 + u], py = t.tile[g * 24 + 8 + u];
-        x0 = fminf(x0, px); x1 = fmaxf(x1, px);
-        y0 = fminf(y0, py); y1 = fmaxf(y1, py);
-      }
-    }
-    const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
-    float r2 = 0.f;
-    for (int u = 0; u < kGroup; ++u) {
-      const int j = g * kGroup + u;
-      if (j < t.m) {
-        const float dx = t.tile[g * 24 + u] - cx, dy = t.tile[g * 24 + 8 + u] - cy;
-        r2 = fmaxf(r2, fmaf(dx, dx, dy * dy));
-      }
-    }
-    t.gcx[g] = cx; t.gcy[g] = cy;
-    t.grad[g] = sqrtf(r2) * 1.000004f + 1e-30f;
-  }
-  __syncwarp();
-}
+constexpr int kCtxBytes = 128;        // PairCtx slot in shared memory
 
 // Candidate sweep over the warp tile (expanded form, packed FFMA2); same contract as
 // nn_candidates<S, true>.
@@ -807,30 +705,12 @@ template <int S>
 __device__ __forceinline__ void eval_mask(const WarpTile& t, unsigned mask, int base_g,
                                           const float (&a)[S], const float (&b)[S],
                                           Candidates<S>& c) {
-#if B200ICP_EVAL_UNROLL2
-  while (mask) {                     // two groups per trip: 12 loads in flight before the math
-    const int g0 = base_g + __ffs(mask) - 1;
-    mask &= mask - 1;
-    if (mask) {
-      const int g1 = base_g + __ffs(mask) - 1;
-      mask &= mask - 1;
-      const GroupRegs r0 = load_group(t, g0);
-      const GroupRegs r1 = load_group(t, g1);
-      eval_group<S>(r0, g0, a, b, c);
-      eval_group<S>(r1, g1, a, b, c);
-    } else {
-      const GroupRegs r0 = load_group(t, g0);
-      eval_group<S>(r0, g0, a, b, c);
-    }
-  }
-#else
   while (mask) {
     const int g = base_g + __ffs(mask) - 1;
     mask &= mask - 1;
     const GroupRegs r = load_group(t, g);
     eval_group<S>(r, g, a, b, c);
   }
-#endif
 }
 
 // Warp-wide min / max of a float through the integer REDUX unit (one instruction instead of a
@@ -940,451 +820,6 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
     eval_mask<S>(t, mask, w << 5, a, b, c);
   }
   return evaluated;
-}
-
-// Inside the best group: FP32 direct-difference distances of its 8 targets, the 3-bit slot
-// packed into the low mantissa bits (relative perturbation <= 2^-20, inside the guard), so
-// the argmin and the runner-up are plain min/max chains.  Returns the winning slot and
-// whether a runner-up lies inside the guard band.
-__device__ __forceinline__ int in_group_argmin(const WarpTile& t, int g, float fx, float fy,
-                                               bool& near_tie) {
-  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * g;
-  const float4 xa = g4[0], xb = g4[1];
-  const float4 ya = g4[2], yb = g4[3];
-  // direct differences, two targets per packed instruction (the sign of dx, dy is irrelevant)
-  const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy);
-  const float2 u0 = __fadd2_rn(make_float2(xa.x, xa.y), nx), v0 = __fadd2_rn(make_float2(ya.x, ya.y), ny);
-  const float2 u1 = __fadd2_rn(make_float2(xa.z, xa.w), nx), v1 = __fadd2_rn(make_float2(ya.z, ya.w), ny);
-  const float2 u2 = __fadd2_rn(make_float2(xb.x, xb.y), nx), v2 = __fadd2_rn(make_float2(yb.x, yb.y), ny);
-  const float2 u3 = __fadd2_rn(make_float2(xb.z, xb.w), nx), v3 = __fadd2_rn(make_float2(yb.z, yb.w), ny);
-  const float2 d01 = __ffma2_rn(v0, v0, __fmul2_rn(u0, u0)), d23 = __ffma2_rn(v1, v1, __fmul2_rn(u1, u1));
-  const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
-  const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
-  unsigned best = 0x7f800000u, second = 0x7f800000u;       // +inf as ordered bit patterns
-#pragma unroll
-  for (int u = 0; u < kGroup; ++u) {
-    const unsigned key = (__float_as_uint(ds[u]) & ~7u) | (unsigned)u;   // d >= 0: bits are ordered
-    second = min(second, max(best, key));
-    best = min(best, key);
-  }
-  const float bd = __uint_as_float(best & ~7u), sd = __uint_as_float(second & ~7u);
-  const float cs = fmaxf(fabsf(fx), fabsf(fy));
-  const float guard = (cs + t.tmax) * 4.76837158e-7f;                // 2^-21 (cs + tmax)
-  const float r = sqrtf(bd) * 1.000004f + guard;
-  near_tie = sd <= r * r * 1.000001f;
-  return (int)(best & 7u);
-}
-
-
-// Per-pair state that is touched once per iteration lives in shared memory, not registers:
-// the sweep needs ~5 registers per source point and every long-lived double evicted from the
-// register file is one more independent FFMA2/FMNMX chain the scheduler can keep in flight.
-struct WarpCtx {
-  double R[4], T[2];          // cumulative pose, src = R A + T
-  double last[4];             // last increment: cos, sin, tx, ty
-  double err, mean_d2, prev_error;
-  double inv_n;
-  int iters, inl;
-  // sweep reuse: cum_move bounds how far any source point has moved since the start (sum of the
-  // per-iteration maximum displacements); pass q may skip its sweep while cum_move <= tile.tpass[q]
-  double cum_move;
-};
-static_assert(sizeof(WarpCtx) <= kCtxBytes, "WarpCtx outgrew its shared-memory slot");
-
-// One pass of the correspondence search: the exact nearest target index j[k] for the SC source
-// points (base + k*32 + lane) of every lane, read from the float64 source state in shared memory.
-// Candidate sweep (FP32, pruned or dense) -> FP32 in-group argmin -> guards -> rare
-// warp-cooperative float64 rescans.  Returns the pair evaluations the sweep executed.
-// Sweep reuse (fused loop): `reuse` skips the sweep and re-decides inside the group stored at the
-// last full sweep; lb[k] (full sweeps only) is a lower bound of the distance from source k to
-// every target OUTSIDE its best group -- the runner-up group of the sweep minus the FP32 error
-// band, and `reach` for the groups the pruned sweep did not visit.  While a point has moved less
-// than (lb - d_nn) / 2 since then, no outside target can have become its nearest neighbour.
-template <int SC, bool PRUNE>
-__device__ __forceinline__ long long warp_search_pass(const WarpTile& t, int base, int n, int m,
-                                                      int lane, int (&j)[SC], bool reuse, bool track,
-                                                      float (&lb)[SC]) {
-  long long evals = 0;
-  float fx[SC], fy[SC];
-#pragma unroll
-  for (int k = 0; k < SC; ++k) {
-    const double2 s = t.src[base + k * 32 + lane];
-    fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
-    lb[k] = -1.f;
-  }
-  Candidates<SC> c;
-  if (reuse) {
-#pragma unroll
-    for (int k = 0; k < SC; ++k) {
-      const int i = base + k * 32 + lane;
-      c.group[k] = i < n ? (t.grp16 ? (int)reinterpret_cast<const unsigned short*>(t.grp)[i] : (int)t.grp[i]) : 0;
-      c.best[k] = 0.f; c.second[k] = CUDART_INF_F;        // cross-group guard: settled by the movement bound
-    }
-  } else if (PRUNE) {
-    bool vld[SC];
-#pragma unroll
-    for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
-    float reach;
-    const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c, track ? 2.0f : 1.0f, reach);
-    evals += (long long)groups * kGroup * min(32 * SC, n - base);
-    if (track) {
-#pragma unroll
-      for (int k = 0; k < SC; ++k) lb[k] = reach * 0.999996f;
-    }
-  } else {
-    warp_candidates<SC>(t, fx, fy, c);
-    evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
-    if (track) {
-#pragma unroll
-      for (int k = 0; k < SC; ++k) lb[k] = CUDART_INF_F;
-    }
-  }
-  if (track && !reuse) {
-#pragma unroll
-    for (int k = 0; k < SC; ++k) {
-      // runner-up group: d^2 >= second + |s|^2 - (FP32 error of the expanded form and of |s|^2)
-      const float cs = fmaxf(fabsf(fx[k]), fabsf(fy[k]));
-      const float ss = fmaf(fx[k], fx[k], fy[k] * fy[k]);
-      const float lo2 = (c.second[k] + ss) - (2.f * expanded_margin(cs, t.tmax) + cs * cs * 4.8e-7f);
-      lb[k] = fminf(lb[k], sqrtf(fmaxf(lo2, 0.f)) * 0.999996f);
-    }
-  }
-  bool amb[SC];
-  bool any_amb = false;
-#pragma unroll
-  for (int k = 0; k < SC; ++k) {
-    bool tie_in;
-    const int slot = in_group_argmin(t, c.group[k], fx[k], fy[k], tie_in);
-    j[k] = c.group[k] * kGroup + slot;
-    amb[k] = (base + k * 32 + lane < n) &&
-             (tie_in || (!reuse && is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax)));
-    any_amb |= amb[k];
-  }
-  if (__any_sync(kFull, any_amb)) {      // rare: warp-cooperative float64 scan
-#pragma unroll
-    for (int k = 0; k < SC; ++k) {
-      unsigned pending = __ballot_sync(kFull, amb[k]);
-      if (!pending) continue;
-      const double2 s = t.src[base + k * 32 + lane];
-      int jk = j[k];
-      while (pending) {
-        const int owner = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const double qx = __shfl_sync(kFull, s.x, owner), qy = __shfl_sync(kFull, s.y, owner);
-        double ld = CUDART_INF;
-        int lj = 0x7fffffff;
-        for (int jj = lane; jj < m; jj += 32) {
-          const double d = dist2_f64(qx, qy, load_point(t.tgt, t.dtype, t.row_off + jj));
-          if (d < ld) { ld = d; lj = jj; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double od = __shfl_xor_sync(kFull, ld, o);
-          const int oj = __shfl_xor_sync(kFull, lj, o);
-          if (od < ld || (od == ld && oj < lj)) { ld = od; lj = oj; }
-        }
-        if (lane == owner) jk = lj;
-      }
-      j[k] = jk;
-    }
-  }
-  if (track && !reuse) {
-#pragma unroll
-    for (int k = 0; k < SC; ++k) {
-      if ((j[k] >> 3) != c.group[k]) lb[k] = -1.f;       // float64 rescan picked another group: no bound
-      const int i = base + k * 32 + lane;
-      if (i < n) {
-        if (t.grp16) reinterpret_cast<unsigned short*>(t.grp)[i] = (unsigned short)(j[k] >> 3);
-        else t.grp[i] = (unsigned char)(j[k] >> 3);
-      }
-    }
-  }
-  return evals;
-}
-
-// Warp-per-pair tile set-up shared by the fused loop and the search-only kernel.
-__device__ __forceinline__ void carve_warp_tile(unsigned char* smem, const KernelArgs& a, WarpTile& t,
-                                                WarpCtx*& ctx) {
-  t.mcap = a.mcap;
-  t.tile = reinterpret_cast<float*>(smem);
-  t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);  // 12*mcap bytes, mcap % 8 == 0
-  ctx = reinterpret_cast<WarpCtx*>(t.src + a.ncap);
-  t.tpass = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx) + kCtxBytes);
-  t.gcx = t.tpass + a.passes;
-  t.gcy = t.gcx + a.mcap / kGroup;
-  t.grad = t.gcy + a.mcap / kGroup;
-  t.grp = reinterpret_cast<unsigned char*>(t.grad + a.mcap / kGroup);     // 2-byte aligned: all counts above are even * 4
-  t.grp16 = a.mcap / kGroup > 256;
-}
-
-// ------------------------------------------------------------------------------------
-// kernel: correspondence search only, one warp per pair (icp.py:37-38): same tile, sweep and
-// exact re-decision as the fused loop, one search, outputs idx and the exact float64 d^2.
-// ------------------------------------------------------------------------------------
-template <int SC, bool PRUNE>
-__global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) nn_warp_kernel(const KernelArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
-  const int64_t p = blockIdx.x;
-  const b200icp_problem& pr = a.prob;
-  int64_t srow, trow;
-  resolve_rows(pr, p, srow, trow);
-  const int n = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
-  const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
-  int32_t* idx_out = a.nn_idx + p * pr.src_pitch;
-  double* d2_out = a.nn_dist2 ? a.nn_dist2 + p * pr.src_pitch : nullptr;
-  if (n <= 0 || m <= 0) {
-    for (int i = lane; i < pr.src_pitch; i += 32) {
-      idx_out[i] = -1;
-      if (d2_out) d2_out[i] = CUDART_INF;
-    }
-    return;
-  }
-  WarpTile t;
-  WarpCtx* ctx;
-  carve_warp_tile(smem_raw, a, t, ctx);
-  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
-  t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
-  warp_stage_targets(t, lane);
-  for (int i = lane; i < a.ncap; i += 32)
-    t.src[i] = i < n ? load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i) : make_double2(t.ox, t.oy);
-  __syncwarp();
-  for (int base = 0; base < n; base += 32 * SC) {
-    int j[SC];
-    float lb_unused[SC];
-    warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j, false, false, lb_unused);
-#pragma unroll
-    for (int k = 0; k < SC; ++k) {
-      const int i = base + k * 32 + lane;
-      if (i < n) {
-        idx_out[i] = j[k];
-        if (d2_out) {
-          const double2 s = t.src[i];
-          d2_out[i] = dist2_f64(s.x, s.y, load_point(t.tgt, t.dtype, t.row_off + j[k]));
-        }
-      }
-    }
-  }
-  for (int i = n + lane; i < pr.src_pitch; i += 32) {
-    idx_out[i] = -1;
-    if (d2_out) d2_out[i] = CUDART_INF;
-  }
-}
-
-template <int SC, bool PRUNE>
-__global__ void __launch_bounds__(32, B200ICP_WARP_MIN_BLOCKS) icp_align_warp_kernel(const KernelArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
-  const int64_t p = blockIdx.x;
-  const b200icp_problem& pr = a.prob;
-  const b200icp_options& op = a.opt;
-  const b200icp_outputs& out = a.out;
-
-  int64_t srow, trow;
-  resolve_rows(pr, p, srow, trow);
-  const int n = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
-  const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
-
-  WarpTile t;
-  WarpCtx* ctx;
-  carve_warp_tile(smem_raw, a, t, ctx);
-  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
-  t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
-
-  const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
-  if (lane == 0) {
-    double R00 = 1.0, R01 = 0.0, R10 = 0.0, R11 = 1.0, T0 = 0.0, T1 = 0.0;
-    if (op.init_pose) {
-      const double* ip = op.init_pose + p * 6;
-      R00 = ip[0]; R01 = ip[1]; R10 = ip[2]; R11 = ip[3]; T0 = ip[4]; T1 = ip[5];
-    }
-    ctx->R[0] = R00; ctx->R[1] = R01; ctx->R[2] = R10; ctx->R[3] = R11;
-    ctx->T[0] = T0; ctx->T[1] = T1;
-    ctx->last[0] = 1.0; ctx->last[1] = 0.0; ctx->last[2] = 0.0; ctx->last[3] = 0.0;
-    ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->prev_error = 0.0;   // icp.py:33
-    ctx->inv_n = n > 0 ? 1.0 / (double)n : 0.0;
-    ctx->iters = 0; ctx->inl = 0;
-    ctx->cum_move = 0.0;
-  }
-  if (lane < a.passes) t.tpass[lane] = -CUDART_INF_F;   // passes <= 32: no pass may skip its first sweep
-  __syncwarp();
-  int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
-  long long evals = 0;          // pair evaluations executed by the sweep (padded targets included)
-
-  if (ran) {
-    warp_stage_targets(t, lane);
-    float smax = 0.f;          // bound of |s - c| over the source points, c = target centroid (sweep reuse)
-    for (int i = lane; i < a.ncap; i += 32) {
-      double2 v = make_double2(t.ox, t.oy);                // padding slots: benign, never used
-      if (i < n) {
-        const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
-        v = q;                                             // icp.py:32  src = copy(A)
-        if (op.init_pose)
-          v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
-                           ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
-        smax = fmaxf(smax, fmaxf(__double2float_ru(fabs(v.x - t.ox)), __double2float_ru(fabs(v.y - t.oy))));
-      }
-      t.src[i] = v;
-    }
-    smax = warp_max_f32(smax) * 1.4142137f;
-    float mv_prev = CUDART_INF_F;      // displacement bound of the previous update
-    double err_prev = 0.0;
-    __syncwarp();
-
-    for (int it = 0; it < op.max_iterations; ++it) {       // icp.py:35
-      int32_t* hist = out.index_history
-          ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
-      double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      // Sweep reuse.  A pass reuses its stored groups whenever the movement bound allows it; the
-      // sweeps compute new bounds (lb, budgets) only once the last update moved the points by less
-      // than half the mean NN distance -- before that no budget would survive the next update.
-      const bool track = a.reuse != 0 && (double)mv_prev < 0.5 * err_prev;
-      for (int base = 0; base < n; base += 32 * SC) {
-        // ---- correspondence search for the SC sources of every lane (icp.py:37-38)
-        int j[SC];
-        float lb[SC];
-        const int pass = base / (32 * SC);
-        const bool reuse = a.reuse != 0 && ctx->cum_move <= (double)t.tpass[pass];
-        evals += warp_search_pass<SC, PRUNE>(t, base, n, m, lane, j, reuse, track, lb);
-        float budget = CUDART_INF_F;
-        // ---- gather (icp.py:39): all SC loads in flight before the first use
-        double2 bm[SC];
-#pragma unroll
-        for (int k = 0; k < SC; ++k) {
-          const int jj = (base + k * 32 + lane < n) ? j[k] : 0;
-          bm[k] = load_point(t.tgt, t.dtype, t.row_off + jj);
-        }
-        const double gate = op.max_corr_dist;
-        const bool use_gate = a.use_gate != 0;
-#pragma unroll
-        for (int k = 0; k < SC; ++k) {
-          const int i = base + k * 32 + lane;
-          if (i < n) {
-            const double2 s = t.src[i];
-            const double2 b = bm[k];
-            const double d2 = dist2_f64(s.x, s.y, b);
-            const double dist = sqrt_f64_fast(d2);
-            if (track && !reuse) budget = fminf(budget, 0.5f * (lb[k] - __double2float_ru(dist) * 1.000001f));
-            if (!use_gate || dist < gate) {
-              const double ax = s.x - t.ox, ay = s.y - t.oy;
-              const double qx = b.x - t.ox, qy = b.y - t.oy;
-              r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
-              r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
-              r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
-              r[8] += dist; r[9] += d2; r[10] += 1.0;
-            }
-            if (idx_out) idx_out[i] = j[k];
-            if (hist) hist[i] = j[k];
-          }
-        }
-        if (track && !reuse) {       // how far the points of this pass may move before it must sweep again
-          budget = warp_min_f32(budget);
-          if (lane == 0) t.tpass[pass] = budget > 0.f ? __double2float_rd(ctx->cum_move + 0.999 * (double)budget) : -CUDART_INF_F;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 11; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r[q] += __shfl_xor_sync(kFull, r[q], o);
-      }
-      const double cnt = r[10];
-      if (cnt < 0.5) {            // every correspondence gated out: stop, search not counted
-        if (lane == 0) { ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->inl = 0; }
-        if (hist) for (int i = lane; i < n; i += 32) hist[i] = -1;
-        break;
-      }
-      const double inv = a.use_gate ? 1.0 / cnt : ctx->inv_n;
-      const double max_ = r[0] * inv, may_ = r[1] * inv;       // centroids rel. origin (icp.py:10-11)
-      const double mbx = r[2] * inv, mby = r[3] * inv;
-      const double mean_error = r[8] * inv;                    // icp.py:48
-      // closed-form 2D Kabsch: the proper rotation the SVD route (icp.py:17-23) returns
-      const double h00 = fma(-r[0], mbx, r[4]), h01 = fma(-r[0], mby, r[5]);
-      const double h10 = fma(-r[1], mbx, r[6]), h11 = fma(-r[1], mby, r[7]);
-      const double num = h01 - h10, den = h00 + h11;
-      const double h2 = fma(num, num, den * den);
-      double cs = 1.0, sn = 0.0;
-      if (h2 > 0.0) {
-        const double rh = rsqrt(h2);
-        cs = den * rh; sn = num * rh;
-      }
-      const double cax = t.ox + max_, cay = t.oy + may_;
-      const double tx = (t.ox + mbx) - (cs * cax - sn * cay);  // icp.py:25
-      const double ty = (t.oy + mby) - (sn * cax + cs * cay);
-      for (int i = lane; i < n; i += 32) {                     // apply (icp.py:45)
-        const double2 s = t.src[i];
-        t.src[i] = make_double2(cs * s.x - sn * s.y + tx, sn * s.x + cs * s.y + ty);
-      }
-      // Upper bound of every point's displacement in this update (sweep reuse): with c the target
-      // centroid, s' - s = (R - I)(s - c) + [(R - I) c + t], so |s' - s| <= |R - I| * smax + |(R - I) c + t|
-      // with |R - I| = sqrt((cos - 1)^2 + sin^2) and smax >= |s - c| for every point (initial maximum,
-      // grown by every displacement bound since).  Rounded up, plus the rounding of the update itself
-      // (a few ulp of the coordinates).  Identical in every lane.
-      float mv = 0.f;
-      if (a.reuse) {
-        const double c1 = cs - 1.0;
-        const double rho = sqrt(fma(c1, c1, sn * sn));
-        const double ddx = fma(c1, t.ox, -sn * t.oy) + tx, ddy = fma(sn, t.ox, c1 * t.oy) + ty;
-        const double ulp = 1.0e-15 * (fabs(t.ox) + fabs(t.oy) + (double)smax + fabs(tx) + fabs(ty));
-        mv = __double2float_ru((rho * (double)smax + sqrt(fma(ddx, ddx, ddy * ddy))) * 1.000001 + ulp);
-        smax = __fadd_ru(smax, mv);
-        mv_prev = mv;
-        err_prev = mean_error;
-      }
-      const bool converged = fabs(ctx->prev_error - mean_error) < op.tolerance;   // icp.py:49-50
-      __syncwarp();
-      if (lane == 0) {            // compose the cumulative pose, record the increment
-        ctx->cum_move += (double)mv * 1.000001;
-        const double R00 = ctx->R[0], R01 = ctx->R[1], R10 = ctx->R[2], R11 = ctx->R[3];
-        const double T0 = ctx->T[0], T1 = ctx->T[1];
-        ctx->R[0] = cs * R00 - sn * R10; ctx->R[1] = cs * R01 - sn * R11;
-        ctx->R[2] = sn * R00 + cs * R10; ctx->R[3] = sn * R01 + cs * R11;
-        ctx->T[0] = cs * T0 - sn * T1 + tx; ctx->T[1] = sn * T0 + cs * T1 + ty;
-        ctx->last[0] = cs; ctx->last[1] = sn; ctx->last[2] = tx; ctx->last[3] = ty;
-        ctx->err = mean_error; ctx->mean_d2 = r[9] * inv; ctx->inl = (int)(cnt + 0.5);
-        ctx->iters = it + 1;
-        ctx->prev_error = mean_error;                          // icp.py:51
-      }
-      __syncwarp();
-      if (converged) break;
-    }
-  }
-
-  const int iters = ctx->iters;
-  if (lane == 0) {
-    double* pt = out.pose_total + p * 6;
-    pt[0] = ctx->R[0]; pt[1] = ctx->R[1]; pt[2] = ctx->R[2]; pt[3] = ctx->R[3];
-    pt[4] = ctx->T[0]; pt[5] = ctx->T[1];
-    if (out.pose_last) {
-      double* pl = out.pose_last + p * 6;
-      pl[0] = ctx->last[0]; pl[1] = -ctx->last[1]; pl[2] = ctx->last[1]; pl[3] = ctx->last[0];
-      pl[4] = ctx->last[2]; pl[5] = ctx->last[3];
-    }
-    out.error[p] = ctx->err;
-    if (out.rmse) out.rmse[p] = sqrt(ctx->mean_d2);
-    if (out.inliers) out.inliers[p] = ctx->inl;
-    out.iterations[p] = iters;
-    if (out.evaluated_pairs) out.evaluated_pairs[p] = evals;
-  }
-  if (idx_out) {
-    for (int i = lane; i < pr.src_pitch; i += 32)
-      if (i >= n || iters == 0) idx_out[i] = -1;
-  }
-  if (out.src_final) {
-    double2* dst = reinterpret_cast<double2*>(out.src_final) + p * pr.src_pitch;
-    for (int i = lane; i < pr.src_pitch; i += 32) {
-      double2 v = make_double2(0.0, 0.0);
-      if (i < n) {
-        if (ran) {
-          v = t.src[i];
-        } else {         // nothing ran: report the (pre-transformed) input
-          const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
-          v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
-                           ctx->R[2] * q.x + ctx->R[3] * q.y + ctx->T[1]);
-        }
-      }
-      dst[i] = v;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1618,7 +1053,7 @@ __device__ __forceinline__ long long pair_search_pass(const PairTile& t, int bas
     const int slot = in_group_decide(t, c.group[k], fx[k], fy[k], tie_in, ubd, los);
     j[k] = c.group[k] * kGroup + slot;
     const bool valid = base + k * 32 + lane < n;
-    amb[k] = valid && (tie_in || (!reuse_grp && is_ambiguous<true>(c.best[k], c.second[k], fx[k], fy[k], t.tmax)));
+    amb[k] = valid && (tie_in || (!reuse_grp && is_ambiguous(c.best[k], c.second[k], fx[k], fy[k], t.tmax)));
     any_amb |= amb[k];
     if (valid) {
       // an ambiguous source is re-decided in float64 below: no FP32 bound describes that decision
@@ -1667,7 +1102,9 @@ __device__ __forceinline__ long long pair_search_pass(const PairTile& t, int bas
 #ifndef B200ICP_PAIR_RESIDENT_WARPS
 #define B200ICP_PAIR_RESIDENT_WARPS 24      // resident warps per SM the kernel is compiled for (register cap)
 #endif
-template <int SC, bool PRUNE, int W>
+// LEAN: float32 tables, no gate, no per-point index outputs (the throughput configuration): the
+// float64 phase is compiled without the corresponding tests and without the inlier count.
+template <int SC, bool PRUNE, int W, bool LEAN>
 __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_align_pair_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = 32 * W;
@@ -1685,7 +1122,7 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
   PairTile t;
   PairCtx* ctx;
   carve_pair_tile(smem_raw, a, W, t, ctx);
-  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
+  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = LEAN ? (int)B200ICP_F32 : pr.dtype;
   t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
 
   const bool ran = n > 0 && m > 0 && op.max_iterations > 0;
@@ -1703,7 +1140,7 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
   }
   for (int q = tid; q < a.passes; q += NT) { t.tgrp[q] = -CUDART_INF_F; t.tnn[q] = -CUDART_INF_F; }
   if (W > 1) __syncthreads(); else __syncwarp();
-  int32_t* idx_out = out.indices ? out.indices + p * pr.src_pitch : nullptr;
+  int32_t* idx_out = (!LEAN && out.indices) ? out.indices + p * pr.src_pitch : nullptr;
   long long evals = 0;
 
   if (ran) {
@@ -1712,7 +1149,7 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
     for (int i = tid; i < a.ncap; i += NT) {
       double2 v = make_double2(t.ox, t.oy);                // padding slots: benign, never used
       if (i < n) {
-        const double2 q = load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i);
+        const double2 q = load_point(pr.src_points, t.dtype, srow * pr.src_pitch + i);
         v = q;                                             // icp.py:32  src = copy(A)
         if (op.init_pose)
           v = make_double2(ctx->R[0] * q.x + ctx->R[1] * q.y + ctx->T[0],
@@ -1737,7 +1174,7 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
     float mv_prev = CUDART_INF_F;      // displacement bound of the previous update
     double prev_error = 0.0;           // icp.py:33
     double cum_move = 0.0;             // sum of the per-iteration displacement bounds
-    const bool use_gate = a.use_gate != 0;
+    const bool use_gate = !LEAN && a.use_gate != 0;
     const double inv_n = 1.0 / (double)n;
 
     for (int it = 0; it < op.max_iterations; ++it) {       // icp.py:35
@@ -1760,7 +1197,7 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
       }
       __syncwarp();
       // ---- phase 2: gather (icp.py:39), exact distances, ONE set of centred sums
-      int32_t* hist = out.index_history
+      int32_t* hist = (!LEAN && out.index_history)
           ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
       double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int pass = warp; pass < a.passes; pass += W) {
@@ -1768,6 +1205,30 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
         if (base >= n) break;
 #pragma unroll
         for (int k0 = 0; k0 < SC; k0 += 2) {
+          if (LEAN && base + (k0 + 2) * 32 <= n && k0 + 2 <= SC) {
+            // both 32-source slots are full (warp-uniform test): straight-line code, no per-lane tests
+            int jj[2];
+            double2 bm[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              jj[u] = (int)t.nnidx[base + (k0 + u) * 32 + lane];
+              bm[u] = load_point(t.tgt, B200ICP_F32, t.row_off + jj[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const double2 s = t.src[base + (k0 + u) * 32 + lane];
+              const double2 b = bm[u];
+              const double d2 = dist2_f64(s.x, s.y, b);
+              const double dist = sqrt_f64_fast(d2);
+              const double ax = s.x - t.ox, ay = s.y - t.oy;
+              const double qx = b.x - t.ox, qy = b.y - t.oy;
+              r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
+              r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
+              r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
+              r[8] += dist; r[9] += d2;
+            }
+            continue;
+          }
           int jj[2];
           double2 bm[2];
 #pragma unroll
@@ -1790,7 +1251,8 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
                 r[0] += ax; r[1] += ay; r[2] += qx; r[3] += qy;
                 r[4] = fma(ax, qx, r[4]); r[5] = fma(ax, qy, r[5]);
                 r[6] = fma(ay, qx, r[6]); r[7] = fma(ay, qy, r[7]);
-                r[8] += dist; r[9] += d2; r[10] += 1.0;
+                r[8] += dist; r[9] += d2;
+                if (!LEAN) r[10] += 1.0;
               }
               if (idx_out) idx_out[i] = jj[u];
               if (hist) hist[i] = jj[u];
@@ -1798,8 +1260,9 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
           }
         }
       }
+      constexpr int NR = LEAN ? 10 : 11;                   // LEAN: no gate, the inlier count is n
 #pragma unroll
-      for (int q = 0; q < 11; ++q) {
+      for (int q = 0; q < NR; ++q) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r[q] += __shfl_xor_sync(kFull, r[q], o);
       }
@@ -1807,19 +1270,19 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
         double* slot = t.red + ((it & 1) * W + warp) * kPairRedStride;
         if (lane == 0) {
 #pragma unroll
-          for (int q = 0; q < 11; ++q) slot[q] = r[q];
+          for (int q = 0; q < NR; ++q) slot[q] = r[q];
         }
         __syncthreads();
         const double* part = t.red + (it & 1) * W * kPairRedStride;
 #pragma unroll
-        for (int q = 0; q < 11; ++q) {
+        for (int q = 0; q < NR; ++q) {
           double acc = part[q];
 #pragma unroll
           for (int w = 1; w < W; ++w) acc += part[w * kPairRedStride + q];
           r[q] = acc;
         }
       }
-      const double cnt = r[10];
+      const double cnt = LEAN ? (double)n : r[10];
       if (cnt < 0.5) {            // every correspondence gated out: stop, search not counted
         if (tid == 0) { ctx->err = CUDART_INF; ctx->mean_d2 = CUDART_INF; ctx->inl = 0; }
         if (hist) for (int i = tid; i < n; i += NT) hist[i] = -1;
@@ -1853,14 +1316,20 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
           }
         }
       }
-      // Upper bound of every point's displacement in this update: see icp_align_warp_kernel.
+      // Upper bound of every point's displacement in this update: with c the target centroid,
+      // s' - s = (R - I)(s - c) + [(R - I) c + t], so |s' - s| <= |R - I| smax + |(R - I) c + t| with
+      // |R - I| = sqrt((cos - 1)^2 + sin^2) and smax >= |s - c| for every point (initial maximum, grown
+      // by every bound since).  The two small vectors are formed in float64 (cancellation), their
+      // norms in float32 and inflated by 1e-5 (a bound need not be tight), plus the rounding of
+      // the update itself (a few float64 ulp of the coordinates).  Identical in every thread.
       float mv = 0.f;
       if (a.reuse) {
         const double c1 = cs - 1.0;
-        const double rho = sqrt(fma(c1, c1, sn * sn));
-        const double ddx = fma(c1, t.ox, -sn * t.oy) + tx, ddy = fma(sn, t.ox, c1 * t.oy) + ty;
-        const double ulp = 1.0e-15 * (fabs(t.ox) + fabs(t.oy) + (double)smax + fabs(tx) + fabs(ty));
-        mv = __double2float_ru((rho * (double)smax + sqrt(fma(ddx, ddx, ddy * ddy))) * 1.000001 + ulp);
+        const float c1f = (float)c1, snf = (float)sn;
+        const float ddx = (float)(fma(c1, t.ox, -sn * t.oy) + tx), ddy = (float)(fma(sn, t.ox, c1 * t.oy) + ty);
+        const float rho = sqrtf(fmaf(c1f, c1f, snf * snf)), dd = sqrtf(fmaf(ddx, ddx, ddy * ddy));
+        const float ulp = 1.0e-15f * (fabsf((float)t.ox) + fabsf((float)t.oy) + smax + fabsf((float)tx) + fabsf((float)ty));
+        mv = fmaf(rho, smax, dd) * 1.00001f + ulp + 1e-30f;
         smax = __fadd_ru(smax, mv);
         mv_prev = mv;
         cum_move += (double)mv * 1.000001;
@@ -1923,6 +1392,61 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
 }
 
 // ------------------------------------------------------------------------------------
+// kernel: correspondence search only, one warp per pair (icp.py:37-38): the tile, sweep and exact
+// re-decision of the fused loop (phase 1), one search, outputs idx and the exact float64 d^2.
+// ------------------------------------------------------------------------------------
+template <int SC, bool PRUNE>
+__global__ void __launch_bounds__(32, B200ICP_PAIR_RESIDENT_WARPS) nn_warp_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int64_t p = blockIdx.x;
+  const b200icp_problem& pr = a.prob;
+  int64_t srow, trow;
+  resolve_rows(pr, p, srow, trow);
+  const int n = pr.src_len ? min(pr.src_len[srow], pr.src_pitch) : pr.src_pitch;
+  const int m = pr.tgt_len ? min(pr.tgt_len[trow], pr.tgt_pitch) : pr.tgt_pitch;
+  int32_t* idx_out = a.nn_idx + p * pr.src_pitch;
+  double* d2_out = a.nn_dist2 ? a.nn_dist2 + p * pr.src_pitch : nullptr;
+  if (n <= 0 || m <= 0) {
+    for (int i = lane; i < pr.src_pitch; i += 32) {
+      idx_out[i] = -1;
+      if (d2_out) d2_out[i] = CUDART_INF;
+    }
+    return;
+  }
+  PairTile t;
+  PairCtx* ctx;
+  carve_pair_tile(smem_raw, a, 1, t, ctx);
+  t.tgt = pr.tgt_points; t.row_off = trow * pr.tgt_pitch; t.dtype = pr.dtype;
+  t.m = m; t.ngroups = (m + kGroup - 1) / kGroup;
+  pair_stage_targets<1>(t, lane, lane, 0);
+  for (int i = lane; i < a.ncap; i += 32)
+    t.src[i] = i < n ? load_point(pr.src_points, pr.dtype, srow * pr.src_pitch + i) : make_double2(t.ox, t.oy);
+  __syncwarp();
+  for (int base = 0; base < n; base += 32 * SC) {
+    float bud_grp, bud_nn;
+    pair_search_pass<SC, PRUNE>(t, base, n, m, lane, false, false, bud_grp, bud_nn);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SC; ++k) {
+      const int i = base + k * 32 + lane;
+      if (i < n) {
+        const int j = (int)t.nnidx[i];
+        idx_out[i] = j;
+        if (d2_out) {
+          const double2 s = t.src[i];
+          d2_out[i] = dist2_f64(s.x, s.y, load_point(t.tgt, t.dtype, t.row_off + j));
+        }
+      }
+    }
+  }
+  for (int i = n + lane; i < pr.src_pitch; i += 32) {
+    idx_out[i] = -1;
+    if (d2_out) d2_out[i] = CUDART_INF;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // kernel: best_fit_transform(A, B) for matched rows (icp.py:5-26), one warp per pair:
 // centroids, centred 2x2 cross-covariance (single pass relative to B's first point),
 // closed-form proper rotation, t = cB - R cA.
@@ -1977,7 +1501,7 @@ __global__ void __launch_bounds__(32) best_fit_warp_kernel(const KernelArgs a) {
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) polar_to_cartesian_kernel(
     const double* __restrict__ raw, const int32_t* __restrict__ raw_len, int raw_pitch,
-    double* __restrict__ xy_out, int32_t* __restrict__ len_out, int out_pitch) {
+    const b200icp_polar_filter f, double* __restrict__ xy_out, int32_t* __restrict__ len_out, int out_pitch) {
   __shared__ int warp_counts[8];
   __shared__ int base_shared;
   const int scan = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1993,14 +1517,14 @@ __global__ void __launch_bounds__(256) polar_to_cartesian_kernel(
     double x = 0.0, y = 0.0;
     if (r < rows) {
       const double quality = src[r * 3 + 0], angle = src[r * 3 + 1], dist = src[r * 3 + 2];
-      const bool front = (angle <= 135.0) || (angle >= 225.0);              // process.py:45
-      keep = dist > 1000.0 && dist < 9000.0 && quality > 10.0 && front;    // process.py:46
+      const bool front = !f.use_arc || (angle <= f.arc_lo) || (angle >= f.arc_hi);   // process.py:45
+      keep = dist > f.min_dist && dist < f.max_dist && quality > f.min_quality && front;   // process.py:46
       if (keep) {
         const double rad = angle * (3.14159265358979323846 / 180.0);       // math.radians
         double sn, cs;
         sincos(rad, &sn, &cs);
         x = dist * cs;                                                      // process.py:48
-        y = -dist * sn;                                                     // process.py:49
+        y = f.y_sign < 0 ? -dist * sn : dist * sn;                          // process.py:49 (realtime_1.py:167: +)
       }
     }
     const unsigned ballot = __ballot_sync(kFull, keep);
@@ -2176,35 +1700,24 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* sink, int inner_
 // host side
 // ------------------------------------------------------------------------------------
 struct LaunchShape {
-  bool expanded;   // search arithmetic: |t|^2 - 2 s.t (default) or direct differences
-  int S;
+  int S;           // CTA-per-pair kernels: source points per lane
   int warps;
   size_t smem;
   int mcap;
 };
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
-
-bool pick_shape(const b200icp_problem* pr, bool align, LaunchShape& ls) {
+bool pick_shape(const b200icp_problem* pr, LaunchShape& ls) {
   const int pitch = pr->src_pitch;
-  int S = env_int("B200ICP_FORCE_S", 0);
-  if (S < 1 || S > kMaxS) {
-    S = (pitch + 127) / 128;                 // aim at <= 4 warps until S saturates
-    if (S < 1) S = 1;
-    if (S > kMaxS) S = kMaxS;
-  }
+  int S = (pitch + 127) / 128;               // aim at <= 4 warps until S saturates
+  if (S < 1) S = 1;
+  if (S > kMaxS) S = kMaxS;
   int warps = (pitch + 32 * S - 1) / (32 * S);
   if (warps < 1) warps = 1;
   if (warps > kMaxWarps) return false;
   ls.S = S;
   ls.warps = warps;
   ls.mcap = (pr->tgt_pitch + kGroup - 1) / kGroup * kGroup;
-  (void)align;
   ls.smem = tile_bytes(ls.mcap);
-  ls.expanded = env_int("B200ICP_SEARCH_DIRECT", 0) == 0;
   return true;
 }
 
@@ -2251,11 +1764,21 @@ int cuda_fail(cudaError_t e, const char* what) {
   return B200ICP_ERR_CUDA;
 }
 
+// One launch per call.  The opt-in to more than 48 KB of dynamic shared memory is made once per
+// kernel and device (the largest size the device allows), not on every launch.
 template <typename Kern>
 int launch_pairs(Kern kern, const LaunchShape& ls, const KernelArgs& args, cudaStream_t st) {
   if (ls.smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls.smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
+    static int opted_in[64] = {0};               // per template instantiation, indexed by device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+      int max_optin = 0;
+      cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
+      if (dev >= 0 && dev < 64) opted_in[dev] = 1;
+    }
   }
   kern<<<(unsigned)args.n_pairs, ls.warps * 32, ls.smem, st>>>(args);
   cudaError_t e = cudaGetLastError();
@@ -2263,74 +1786,13 @@ int launch_pairs(Kern kern, const LaunchShape& ls, const KernelArgs& args, cudaS
   return B200ICP_OK;
 }
 
-// Warp-per-pair launch shape: the pruned sweep works in passes of 32*SP consecutive sources
-// (SP = 2), the dense sweep in passes of 32*SC sources chosen to minimise padding.
-struct WarpShape {
-  int S;
-  bool prune;
-};
-
-WarpShape pick_warp_shape(const b200icp_problem* prob, bool dense, const LaunchShape& ls, KernelArgs& args,
-                          LaunchShape& ws) {
-  WarpShape w;
-  w.prune = !dense;
-  if (w.prune) {
-    w.S = env_int("B200ICP_PRUNE_S", 2);
-    if (w.S < 1 || w.S > 4) w.S = 2;
-  } else {
-    w.S = env_int("B200ICP_FORCE_SC", 0);
-    if (w.S != 2 && w.S != 4 && w.S != 6 && w.S != 8 && w.S != 12) {
-      // cost model: padded source slots, plus a per-sweep overhead that shrinks with the pass
-      // width (target LDS and loop control are shared by the SC sources of a lane).  SC = 12 is
-      // compiled but never chosen: one 12-wide pass measured slower than two 6-wide passes on
-      // B200 (profiles/r1_kernel_tuning.md).
-      const int cand[4] = {8, 6, 4, 2};
-      double best_cost = 1e30;
-      w.S = 8;
-      for (int q = 0; q < 4; ++q) {
-        const int span = 32 * cand[q];
-        const int slots = (prob->src_pitch + span - 1) / span * span;
-        const double cost = slots * (1.0 + 1.0 / cand[q]);
-        if (cost < best_cost) { best_cost = cost; w.S = cand[q]; }
-      }
-    }
-  }
-  args.ncap = (prob->src_pitch + 32 * w.S - 1) / (32 * w.S) * (32 * w.S);
-  args.passes = args.ncap / (32 * w.S);
-  ws = ls;
-  ws.warps = 1;
-  ws.smem = warp_tile_bytes(ls.mcap, args.ncap, prob->src_pitch, args.passes, args.reuse != 0);
-  return w;
-}
-
-#define B200ICP_DISPATCH_WARP(KERNEL, DENSE)                                             \
-  {                                                                                      \
-    LaunchShape ws;                                                                      \
-    const WarpShape w = pick_warp_shape(prob, DENSE, ls, args, ws);                      \
-    if (w.prune) {                                                                       \
-      switch (w.S) {                                                                     \
-        case 1: return launch_pairs(KERNEL<1, true>, ws, args, st);                      \
-        case 2: return launch_pairs(KERNEL<2, true>, ws, args, st);                      \
-        case 3: return launch_pairs(KERNEL<3, true>, ws, args, st);                      \
-        default: return launch_pairs(KERNEL<4, true>, ws, args, st);                     \
-      }                                                                                  \
-    }                                                                                    \
-    switch (w.S) {                                                                       \
-      case 2: return launch_pairs(KERNEL<2, false>, ws, args, st);                       \
-      case 4: return launch_pairs(KERNEL<4, false>, ws, args, st);                       \
-      case 6: return launch_pairs(KERNEL<6, false>, ws, args, st);                       \
-      case 8: return launch_pairs(KERNEL<8, false>, ws, args, st);                       \
-      default: return launch_pairs(KERNEL<12, false>, ws, args, st);                     \
-    }                                                                                    \
-  }
-
-// W-warps-per-pair fused kernel: passes of 64 sources (pruned sweep) or 128 sources (dense sweep),
+// W-warps-per-pair fused kernel: passes of 64 sources (pruned sweep) or 192 sources (dense sweep),
 // dealt round-robin to W <= 4 warps.  W = the warp count in 2..4 that leaves the fewest idle
 // warp-rounds, the smallest on ties: measured on B200 (profiles/r2_kernel_tuning.md) two warps beat
 // one (shared tile: 24 instead of 18 resident warps per SM) and three or four (the redundant pose
 // solve and the wait at the cross-warp sum grow with W): 360 points = 6 pruned passes on 2 warps,
-// 3 dense passes on 3.
-constexpr int kPairS = 2, kPairDenseS = 4, kPairMaxWarps = 4;
+// 2 dense passes on 2.
+constexpr int kPairS = 2, kPairDenseS = 6, kPairMaxWarps = 4;
 
 int pair_warps_for(int passes, int forced) {
   if (passes < 1) passes = 1;
@@ -2352,10 +1814,15 @@ int launch_pair_kernel(const b200icp_problem* prob, const LaunchShape& ls, Kerne
   LaunchShape ps = ls;
   ps.warps = pair_warps_for(args.passes, forced_warps);
   ps.smem = pair_tile_bytes(ls.mcap, args.ncap, args.passes, ps.warps);
-#define B200ICP_PAIR_CASE(W)                                                                      \
-  case W:                                                                                         \
-    return dense ? launch_pairs(icp_align_pair_kernel<kPairDenseS, false, W>, ps, args, st)       \
-                 : launch_pairs(icp_align_pair_kernel<kPairS, true, W>, ps, args, st);
+  // LEAN: the throughput configuration (float32 tables, no gate, no per-point index outputs)
+  const bool lean = prob->dtype == B200ICP_F32 && !args.use_gate && !args.out.indices && !args.out.index_history;
+#define B200ICP_PAIR_CASE(W)                                                                            \
+  case W:                                                                                               \
+    if (lean)                                                                                           \
+      return dense ? launch_pairs(icp_align_pair_kernel<kPairDenseS, false, W, true>, ps, args, st)     \
+                   : launch_pairs(icp_align_pair_kernel<kPairS, true, W, true>, ps, args, st);          \
+    return dense ? launch_pairs(icp_align_pair_kernel<kPairDenseS, false, W, false>, ps, args, st)      \
+                 : launch_pairs(icp_align_pair_kernel<kPairS, true, W, false>, ps, args, st);
   switch (ps.warps) {
     B200ICP_PAIR_CASE(1)
     B200ICP_PAIR_CASE(2)
@@ -2365,6 +1832,33 @@ int launch_pair_kernel(const b200icp_problem* prob, const LaunchShape& ls, Kerne
   }
 #undef B200ICP_PAIR_CASE
 }
+
+int launch_nn_warp_kernel(const b200icp_problem* prob, const LaunchShape& ls, KernelArgs& args, bool dense,
+                          cudaStream_t st) {
+  const int S = dense ? kPairDenseS : kPairS;
+  args.ncap = (prob->src_pitch + 32 * S - 1) / (32 * S) * (32 * S);
+  args.passes = args.ncap / (32 * S);
+  LaunchShape ps = ls;
+  ps.warps = 1;
+  ps.smem = pair_tile_bytes(ls.mcap, args.ncap, args.passes, 1);
+  return dense ? launch_pairs(nn_warp_kernel<kPairDenseS, false>, ps, args, st)
+               : launch_pairs(nn_warp_kernel<kPairS, true>, ps, args, st);
+}
+
+// Which kernel family for a batch?  b200icp.h: B200ICP_FLAG_WARP_KERNEL / _CTA_KERNEL, else by size.
+bool use_cta_kernel(int64_t n_pairs, int flags, bool wants_stats) {
+  if (flags & B200ICP_FLAG_WARP_KERNEL) return false;
+  if (flags & B200ICP_FLAG_CTA_KERNEL) return true;
+  return n_pairs <= kAutoCtaPairs && !(flags & B200ICP_FLAG_DENSE_SWEEP) && !wants_stats;
+}
+
+#define B200ICP_DISPATCH_CTA(KERNEL)                                         \
+  switch (ls.S) {                                                            \
+    case 1: return launch_pairs(KERNEL<1>, ls, args, st);                    \
+    case 2: return launch_pairs(KERNEL<2>, ls, args, st);                    \
+    case 3: return launch_pairs(KERNEL<3>, ls, args, st);                    \
+    default: return launch_pairs(KERNEL<4>, ls, args, st);                   \
+  }
 
 }  // namespace
 
@@ -2381,13 +1875,13 @@ int b200icp_max_src_pitch(void) { return kMaxSrcPitch; }
 int b200icp_max_tgt_pitch(void) { return kMaxTgtPitch; }
 
 int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs, int32_t* idx_out,
-                     double* dist2_out, void* stream) {
+                     double* dist2_out, int32_t flags, void* stream) {
   int rc = check_problem(prob, n_pairs);
   if (rc != B200ICP_OK) return rc;
   if (!idx_out) { set_error("idx_out is NULL"); return B200ICP_ERR_INVALID_ARGUMENT; }
   if (n_pairs == 0) return B200ICP_OK;
   LaunchShape ls;
-  if (!pick_shape(prob, false, ls)) { set_error("unsupported src_pitch"); return B200ICP_ERR_UNSUPPORTED_SHAPE; }
+  if (!pick_shape(prob, ls)) { set_error("unsupported src_pitch"); return B200ICP_ERR_UNSUPPORTED_SHAPE; }
   KernelArgs args;
   memset(&args, 0, sizeof(args));
   args.prob = *prob;
@@ -2396,25 +1890,10 @@ int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs, int32_t* idx_
   args.n_pairs = n_pairs;
   args.mcap = ls.mcap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define B200ICP_DISPATCH(KERNEL)                                                        \
-  switch (ls.S * 2 + (ls.expanded ? 1 : 0)) {                                          \
-    case 2: return launch_pairs(KERNEL<1, false>, ls, args, st);                       \
-    case 3: return launch_pairs(KERNEL<1, true>, ls, args, st);                        \
-    case 4: return launch_pairs(KERNEL<2, false>, ls, args, st);                       \
-    case 5: return launch_pairs(KERNEL<2, true>, ls, args, st);                        \
-    case 6: return launch_pairs(KERNEL<3, false>, ls, args, st);                       \
-    case 7: return launch_pairs(KERNEL<3, true>, ls, args, st);                        \
-    case 8: return launch_pairs(KERNEL<4, false>, ls, args, st);                       \
-    default: return launch_pairs(KERNEL<4, true>, ls, args, st);                       \
-  }
   // same rule as the fused loop: CTA per pair below the batch size that fills the GPU with one-warp CTAs
-  int cta = env_int("B200ICP_NN_BLOCK", -1);
-  if (cta < 0) cta = n_pairs <= kAutoCtaPairs ? 1 : 0;
-  if (cta == 0) {
-    const bool dense = env_int("B200ICP_PRUNE", 1) == 0;
-    B200ICP_DISPATCH_WARP(nn_warp_kernel, dense)
-  }
-  B200ICP_DISPATCH(nn_pair_kernel)
+  if (!use_cta_kernel(n_pairs, flags, false))
+    return launch_nn_warp_kernel(prob, ls, args, (flags & B200ICP_FLAG_DENSE_SWEEP) != 0, st);
+  B200ICP_DISPATCH_CTA(nn_pair_kernel)
 }
 
 int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200icp_options* opt,
@@ -2429,7 +1908,7 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   if (opt->max_iterations < 0) { set_error("max_iterations < 0"); return B200ICP_ERR_INVALID_ARGUMENT; }
   if (n_pairs == 0) return B200ICP_OK;
   LaunchShape ls;
-  if (!pick_shape(prob, true, ls)) { set_error("unsupported src_pitch"); return B200ICP_ERR_UNSUPPORTED_SHAPE; }
+  if (!pick_shape(prob, ls)) { set_error("unsupported src_pitch"); return B200ICP_ERR_UNSUPPORTED_SHAPE; }
   KernelArgs args;
   memset(&args, 0, sizeof(args));
   args.prob = *prob;
@@ -2438,25 +1917,16 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   args.n_pairs = n_pairs;
   args.mcap = ls.mcap;
   args.use_gate = (opt->max_corr_dist > 0.0 && std::isfinite(opt->max_corr_dist)) ? 1 : 0;
-  args.reuse = (env_int("B200ICP_REUSE", 1) != 0 && !(opt->flags & B200ICP_FLAG_NO_SWEEP_REUSE)) ? 1 : 0;
+  args.reuse = (opt->flags & B200ICP_FLAG_NO_SWEEP_REUSE) ? 0 : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Which fused kernel?  One warp per pair has the best throughput once the pairs fill the GPU
-  // (148 SMs x 16 one-warp CTAs); below that a pair's latency is what counts and the CTA-per-pair
+  // Which fused kernel?  W warps per pair sharing one tile has the best throughput once the pairs
+  // fill the GPU (148 SMs x 12 CTAs); below that a pair's latency is what counts and the CTA-per-pair
   // kernel (up to 8 warps on one pair) is 2-4.6x faster: 0.14 vs 0.52 ms for one 160 x 1,000
   // scan-to-local-map registration, crossover near 1,000 pairs of 360 x 360 (tools/latency_single.py).
-  int cta = -1;
-  if (opt->flags & B200ICP_FLAG_WARP_KERNEL) cta = 0;
-  else if (opt->flags & B200ICP_FLAG_CTA_KERNEL) cta = 1;
-  else cta = env_int("B200ICP_ALIGN_BLOCK", -1);
-  if (cta < 0)
-    cta = (n_pairs <= kAutoCtaPairs && !(opt->flags & B200ICP_FLAG_DENSE_SWEEP) && !out->evaluated_pairs) ? 1 : 0;
-  if (cta == 0) {
-    const bool dense = env_int("B200ICP_PRUNE", 1) == 0 || (opt->flags & B200ICP_FLAG_DENSE_SWEEP);
-    if (!(opt->flags & B200ICP_FLAG_LEGACY_WARP_KERNEL))
-      return launch_pair_kernel(prob, ls, args, dense, (opt->flags >> B200ICP_FLAG_PAIR_WARPS_SHIFT) & 7, st);
-    B200ICP_DISPATCH_WARP(icp_align_warp_kernel, dense)
-  }
-  B200ICP_DISPATCH(icp_align_kernel)
+  if (!use_cta_kernel(n_pairs, opt->flags, out->evaluated_pairs != nullptr))
+    return launch_pair_kernel(prob, ls, args, (opt->flags & B200ICP_FLAG_DENSE_SWEEP) != 0,
+                              (opt->flags >> B200ICP_FLAG_PAIR_WARPS_SHIFT) & 7, st);
+  B200ICP_DISPATCH_CTA(icp_align_kernel)
 }
 
 int b200icp_best_fit_batch(const b200icp_problem* prob, int64_t n_pairs, double* pose_out, void* stream) {
@@ -2477,13 +1947,18 @@ int b200icp_best_fit_batch(const b200icp_problem* prob, int64_t n_pairs, double*
 }
 
 int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_t n_scans,
-                               int32_t raw_pitch, double* xy_out, int32_t* len_out,
-                               int32_t out_pitch, void* stream) {
+                               int32_t raw_pitch, const b200icp_polar_filter* filter, double* xy_out,
+                               int32_t* len_out, int32_t out_pitch, void* stream) {
   if (!raw || !xy_out || !len_out) { set_error("NULL pointer"); return B200ICP_ERR_INVALID_ARGUMENT; }
   if (n_scans < 0 || raw_pitch < 1 || out_pitch < 1) { set_error("bad size"); return B200ICP_ERR_INVALID_ARGUMENT; }
   if (n_scans == 0) return B200ICP_OK;
+  b200icp_polar_filter f;                        // process.py:45-46,49 (canonical)
+  f.min_dist = 1000.0; f.max_dist = 9000.0; f.min_quality = 10.0; f.arc_lo = 135.0; f.arc_hi = 225.0;
+  f.use_arc = 1; f.y_sign = -1;
+  if (filter) f = *filter;
+  if (f.y_sign != 1 && f.y_sign != -1) { set_error("polar filter: y_sign must be +1 or -1"); return B200ICP_ERR_INVALID_ARGUMENT; }
   polar_to_cartesian_kernel<<<n_scans, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      raw, raw_len, raw_pitch, xy_out, len_out, out_pitch);
+      raw, raw_len, raw_pitch, f, xy_out, len_out, out_pitch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "polar_to_cartesian launch");
   return B200ICP_OK;

@@ -209,11 +209,12 @@ def _check_out(out: "AlignResult", b: int, src_pitch: int, max_iterations: int, 
 def nn_search(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
               pairing: str = "rowwise", src_row=None, tgt_row=None, first_pair: int = 0,
               want_dist2: bool = True, out_idx=None, out_dist2=None, validate_rows: bool = False,
-              stream=None):
+              kernel: str = "auto", dense_sweep: bool = False, stream=None):
     """Nearest target index for every source point of every pair.
 
     Replaces ``KDTree(B).query(src)`` (icp.py:37-38): returns (idx int32 [B,pitch],
-    dist2 float64 [B,pitch] or None); idx = -1 beyond a row's length.
+    dist2 float64 [B,pitch] or None); idx = -1 beyond a row's length.  ``kernel``: "auto" (by
+    batch size), "warp" or "cta"; ``dense_sweep`` disables the culling of target groups (A/B).
     """
     pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
     b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
@@ -228,7 +229,9 @@ def nn_search(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None,
     if d2 is None and want_dist2:
         d2 = torch.empty((b, src.pitch), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().b200icp_nn_batch(C.byref(pr), b, _ptr(idx), _ptr(d2), _stream_ptr(stream))
+        flags = ((_cabi.FLAG_DENSE_SWEEP if dense_sweep else 0) |
+                 {"auto": 0, "warp": _cabi.FLAG_WARP_KERNEL, "cta": _cabi.FLAG_CTA_KERNEL}[kernel])
+        rc = _cabi.lib().b200icp_nn_batch(C.byref(pr), b, _ptr(idx), _ptr(d2), flags, _stream_ptr(stream))
     _cabi.check(rc, "b200icp_nn_batch")
     return idx, d2
 
@@ -271,8 +274,8 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     ``sweep_reuse=False`` sweeps every pass in every iteration instead of skipping the sweep of a
     pass whose points provably keep their nearest neighbour's group (identical results; A/B knob).
     ``kernel``: "auto" (CTA-per-pair fused kernel up to 2,048 pairs -- lowest latency --, the
-    W-warps-per-pair throughput kernel above), "warp" (throughput kernel), "cta", or "legacy-warp"
-    (the round-1 one-warp-per-pair kernel, A/B only).  ``pair_warps`` forces W (1..4; 0 = auto).
+    W-warps-per-pair throughput kernel above), "warp" (throughput kernel) or "cta".
+    ``pair_warps`` forces W (1..4; 0 = auto).
     """
     pr = _problem(src, tgt, pairing, src_row, tgt_row, first_pair)
     b = _default_pairs(src, tgt, pairing, src_row, first_pair) if n_pairs is None else int(n_pairs)
@@ -287,8 +290,7 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     opt = _cabi.Options()
     opt.max_iterations = int(max_iterations)
     opt.flags = ((_cabi.FLAG_DENSE_SWEEP if dense_sweep else 0) | (0 if sweep_reuse else _cabi.FLAG_NO_SWEEP_REUSE) |
-                 {"auto": 0, "warp": _cabi.FLAG_WARP_KERNEL, "cta": _cabi.FLAG_CTA_KERNEL,
-                  "legacy-warp": _cabi.FLAG_WARP_KERNEL | _cabi.FLAG_LEGACY_WARP_KERNEL}[kernel] |
+                 {"auto": 0, "warp": _cabi.FLAG_WARP_KERNEL, "cta": _cabi.FLAG_CTA_KERNEL}[kernel] |
                  ((int(pair_warps) & 7) << _cabi.FLAG_PAIR_WARPS_SHIFT))
     opt.tolerance = float(tolerance)
     opt.max_corr_dist = 0.0 if max_corr_dist is None else float(max_corr_dist)
@@ -325,10 +327,21 @@ def best_fit(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None, s
     return pose
 
 
+POLAR_FILTERS = {
+    # name: (min_dist, max_dist, min_quality, arc_lo, arc_hi, use_arc, y_sign)
+    "process": (1000.0, 9000.0, 10.0, 135.0, 225.0, 1, -1),        # duc/ICP_LIDAR/process.py:45-49 (canonical)
+    "slam_offline": (0.0, 10000.0, 13.0, 135.0, 225.0, 1, -1),      # duc/ICP_LIDAR/slam_offline.py:68-72
+    "realtime_2": (0.0, 5000.0, 5.0, 135.0, 225.0, 0, -1),          # duc/code python/realtime_2.py:159-163
+    "realtime_1": (0.0, 5000.0, 5.0, 135.0, 225.0, 0, 1),           # duc/code python/realtime_1.py:164-167, b.py:173-177
+}
+
+
 def polar_to_cartesian(raw: torch.Tensor, raw_len: Optional[torch.Tensor] = None,
-                       out_pitch: Optional[int] = None, stream=None) -> ScanTable:
+                       out_pitch: Optional[int] = None, stream=None, filter="process") -> ScanTable:
     """Device scan preparation (process.py:38-52): raw [S, pitch, 3] float64 rows of
-    (quality, angle_deg, distance_mm) -> filtered Cartesian ScanTable (float64)."""
+    (quality, angle_deg, distance_mm) -> filtered Cartesian ScanTable (float64).  ``filter``: the name
+    of one of the reference's copies of the function (POLAR_FILTERS) or a 7-tuple
+    (min_dist, max_dist, min_quality, arc_lo, arc_hi, use_arc, y_sign)."""
     if raw.dim() != 3 or raw.shape[2] != 3 or raw.dtype != torch.float64:
         raise ValueError("raw must be float64 [scans, pitch, 3]")
     _require_cuda(raw, "raw")
@@ -337,7 +350,9 @@ def polar_to_cartesian(raw: torch.Tensor, raw_len: Optional[torch.Tensor] = None
     xy = torch.empty((s, out_pitch, 2), dtype=torch.float64, device=raw.device)
     lens = torch.empty(s, dtype=torch.int32, device=raw.device)
     with torch.cuda.device(raw.device):
-        rc = _cabi.lib().b200icp_polar_to_cartesian(_ptr(raw), _ptr(raw_len), s, pitch, _ptr(xy),
+        fv = POLAR_FILTERS[filter] if isinstance(filter, str) else tuple(filter)
+        pf = _cabi.PolarFilter(float(fv[0]), float(fv[1]), float(fv[2]), float(fv[3]), float(fv[4]), int(fv[5]), int(fv[6]))
+        rc = _cabi.lib().b200icp_polar_to_cartesian(_ptr(raw), _ptr(raw_len), s, pitch, C.byref(pf), _ptr(xy),
                                                     _ptr(lens), out_pitch, _stream_ptr(stream))
     _cabi.check(rc, "b200icp_polar_to_cartesian")
     return ScanTable(xy, lens)

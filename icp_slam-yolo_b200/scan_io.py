@@ -85,7 +85,9 @@ def raw_table(scans: Sequence[np.ndarray], pitch: Optional[int] = None, pin: boo
     return tr, tl
 
 
-def prepare_scans(scans: Sequence[np.ndarray], device="cuda", out_pitch: Optional[int] = None) -> ScanTable:
-    """Polar scans -> filtered Cartesian ScanTable, computed on the device."""
+def prepare_scans(scans: Sequence[np.ndarray], device="cuda", out_pitch: Optional[int] = None,
+                  filter="process") -> ScanTable:
+    """Polar scans -> filtered Cartesian ScanTable, computed on the device.  ``filter``: which of
+    the reference's copies of polar_to_cartesian_3d (registration.POLAR_FILTERS)."""
     raw, lens = raw_table(scans)
-    return polar_to_cartesian(raw.to(device), lens.to(device), out_pitch=out_pitch)
+    return polar_to_cartesian(raw.to(device), lens.to(device), out_pitch=out_pitch, filter=filter)

@@ -98,16 +98,18 @@ typedef struct b200icp_problem {
                                           since then against the gap to the nearest outside target);
                                           the correspondences are identical either way.            */
 
-#define B200ICP_FLAG_WARP_KERNEL 4  /* force the warp-per-pair fused kernel                         */
-#define B200ICP_FLAG_CTA_KERNEL 8   /* force the CTA-per-pair fused kernel.  Default: chosen by the
-                                       batch size -- one warp per pair has the higher throughput once
-                                       the pairs fill the GPU (> 2,048), a CTA of up to 8 warps per pair
-                                       the lower latency below that (one registration per frame).
-                                       Identical correspondences; poses agree to ~1e-12.          */
-
-#define B200ICP_FLAG_LEGACY_WARP_KERNEL 16 /* A/B only: the round-1 one-warp-per-pair fused kernel
-                                              instead of the W-warps-per-pair one (same results up
-                                              to the order of the float64 sums, ~1e-12)               */
+#define B200ICP_FLAG_WARP_KERNEL 4  /* force the throughput kernel (W warps per pair, shared tile)  */
+#define B200ICP_FLAG_CTA_KERNEL 8   /* force the latency kernel (one CTA of up to 8 warps per pair).
+                                       Default: chosen by the batch size -- the throughput kernel once
+                                       the pairs fill the GPU (> 2,048), the latency kernel below that
+                                       (one registration per frame).
+                                       BATCH-SIZE DEPENDENCE: the two kernels find identical
+                                       correspondences and iteration counts but add the float64 sums in
+                                       a different order, so the pose bits of one pair may differ by
+                                       ~1e-12 (relative) between a call of <= 2,048 pairs and a larger
+                                       one.  Callers that need bit-stable poses across batch sizes
+                                       force one kernel with these flags (HostPipeline does, on the
+                                       size of the whole batch).                                   */
 #define B200ICP_FLAG_PAIR_WARPS_SHIFT 8    /* tuning: bits 8..10 = warps per pair (1..4) of the
                                               throughput kernel; 0 = chosen from the number of passes */
 
@@ -153,7 +155,8 @@ int b200icp_max_tgt_pitch(void);
  *   dist2_out [n_pairs][src_pitch] float64 squared distance (NULL to skip)
  */
 int b200icp_nn_batch(const b200icp_problem* prob, int64_t n_pairs,
-                     int32_t* idx_out, double* dist2_out, void* stream);
+                     int32_t* idx_out, double* dist2_out, int32_t flags /* B200ICP_FLAG_DENSE_SWEEP,
+                     _WARP_KERNEL, _CTA_KERNEL; 0 = defaults */, void* stream);
 
 /*
  * Whole ICP loop per pair, fused on the device (no host round trips).
@@ -179,11 +182,23 @@ int b200icp_best_fit_batch(const b200icp_problem* prob, int64_t n_pairs, double*
  * Replaces polar_to_cartesian_3d (duc/ICP_LIDAR/process.py:38-52).
  *   raw      [n_scans][raw_pitch][3] float64 rows (quality, angle_deg, distance_mm)
  *   raw_len  [n_scans] valid rows per scan
+ *   filter   NULL = the canonical thresholds of process.py:45-46; the reference's other copies of
+ *            the function differ only in these constants: slam_offline.py:68-69 (0 < d < 10000,
+ *            q > 13, arc), realtime_2.py:160-161 (0 < d < 5000, q > 5, no arc), realtime_1.py:164-167
+ *            and b.py:173-177 (as realtime_2 with y = +d sin)
  *   xy_out   [n_scans][out_pitch][2] float64;  len_out [n_scans]
  */
+typedef struct b200icp_polar_filter {
+  double min_dist, max_dist;    /* keep min_dist < distance < max_dist   (process.py:46: 1000, 9000) */
+  double min_quality;           /* keep quality > min_quality            (process.py:46: 10)         */
+  double arc_lo, arc_hi;        /* keep angle <= arc_lo or angle >= arc_hi (process.py:45: 135, 225) */
+  int32_t use_arc;              /* 0: no arc test                                                    */
+  int32_t y_sign;               /* -1: y = -d sin (process.py:49);  +1: y = +d sin                   */
+} b200icp_polar_filter;
+
 int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_t n_scans,
-                               int32_t raw_pitch, double* xy_out, int32_t* len_out,
-                               int32_t out_pitch, void* stream);
+                               int32_t raw_pitch, const b200icp_polar_filter* filter, double* xy_out,
+                               int32_t* len_out, int32_t out_pitch, void* stream);
 
 /* ---- scan-to-map ICP: a scan of a few thousand points against a map of millions, sharded
  * contiguously across GPUs (one process per GPU).  The scan-to-local-map call shape of

@@ -217,6 +217,28 @@ def polar_to_cartesian(scan):
     return np.stack([x, y, np.zeros_like(x)], axis=1)
 
 
+# The reference's other copies of polar_to_cartesian_3d differ from process.py:45-49 only in
+# constants: (min_dist, max_dist, min_quality, use_arc, y_sign)
+POLAR_VARIANTS = {
+    "process": (1000, 9000, 10, True, -1),          # duc/ICP_LIDAR/process.py:45-49 (canonical)
+    "slam_offline": (0, 10000, 13, True, -1),       # duc/ICP_LIDAR/slam_offline.py:68-72
+    "realtime_2": (0, 5000, 5, False, -1),          # duc/code python/realtime_2.py:159-163
+    "realtime_1": (0, 5000, 5, False, 1),           # duc/code python/realtime_1.py:164-167, b.py:173-177
+}
+
+
+def polar_to_cartesian_variant(scan, variant):
+    """Row loop of the named copy of polar_to_cartesian_3d (same statements, its constants)."""
+    lo, hi, qmin, use_arc, ysign = POLAR_VARIANTS[variant]
+    out = []
+    for quality, angle, distance in scan:
+        front = (not use_arc) or (angle <= 135) or (angle >= 225)
+        if distance > lo and distance < hi and quality > qmin and front:
+            a = math.radians(angle)
+            out.append([distance * math.cos(a), ysign * distance * math.sin(a), 0.0])
+    return np.array(out) if out else np.zeros((0, 3))
+
+
 def scan_path(directory, k):
     """Scan_data_1 mixes ``Scan_data_{k}.npy`` (k<=219) and ``scan_data_{k}.npy``
     (SURVEY.md §8 a1); resolve either spelling."""

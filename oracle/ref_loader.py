@@ -1,7 +1,11 @@
-"""Import the UNMODIFIED reference ``labels_segmentation/icp.py`` (build container only).
+"""Import the UNMODIFIED reference ``labels_segmentation/icp.py``.
 
-TEST INFRASTRUCTURE.  ``/root/reference`` exists only in the build container,
-never on the GPU box; callers must check :func:`reference_available` first.
+TEST INFRASTRUCTURE.  ``/root/reference`` exists only in the build container, never on the GPU
+box.  ``make -C oracle ref`` (run by ``__graft_entry__.build()`` when the reference tree is
+present) places a byte-identical copy of that one file at ``oracle/_ref/icp.py``; the directory is
+git-ignored (no reference source enters the history) but travels to the GPU box with the other
+built artefacts, so that ``bench.py``'s CPU arm can time the reference itself there.  Callers must
+check :func:`reference_available` first.
 The reference module imports ``matplotlib.pyplot`` (icp.py:2) and runs a demo
 with ``plt.show()`` at import time (icp.py:55-78); matplotlib is not installed
 here, so a no-op stub is registered for the duration of the import.
@@ -14,12 +18,19 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("ICP_REFERENCE_ROOT", "/root/reference")
-_ICP_PATH = os.path.join(REFERENCE_ROOT, "labels_segmentation", "icp.py")
+_ICP_TREE = os.path.join(REFERENCE_ROOT, "labels_segmentation", "icp.py")
+_ICP_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "icp.py")
+_ICP_PATH = _ICP_TREE if os.path.isfile(_ICP_TREE) else _ICP_COPY
 _cached = None
 
 
 def reference_available() -> bool:
     return os.path.isfile(_ICP_PATH)
+
+
+def reference_icp_path() -> str:
+    """Where the unmodified icp.py is loaded from (the tree, else the build-time copy)."""
+    return _ICP_PATH
 
 
 def scan_dir(name="Scan_data_1") -> str:

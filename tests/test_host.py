@@ -36,17 +36,20 @@ def test_cabi_exports_every_declared_symbol(pkg):
 def test_cabi_rejects_bad_arguments_without_touching_the_gpu(pkg):
     from icp_slam_yolo_b200 import _cabi
     L = pkg.lib()
-    assert L.b200icp_nn_batch(None, 1, None, None, None) == 1
+    assert L.b200icp_nn_batch(None, 1, None, None, 0, None) == 1
     pr = _cabi.Problem()
-    assert L.b200icp_nn_batch(ctypes.byref(pr), 1, None, None, None) == 1
+    assert L.b200icp_nn_batch(ctypes.byref(pr), 1, None, None, 0, None) == 1
     assert b"NULL" in L.b200icp_last_error()
     pr.src_points = pr.tgt_points = 4096
     pr.src_pitch, pr.tgt_pitch, pr.dtype = 2000, 16, _cabi.F64
-    assert L.b200icp_nn_batch(ctypes.byref(pr), 1, ctypes.c_void_p(4096), None, None) == 2
+    assert L.b200icp_nn_batch(ctypes.byref(pr), 1, ctypes.c_void_p(4096), None, 0, None) == 2
     pr.src_pitch, pr.pairing, pr.n_rows = 16, _cabi.PAIR_TRIANGLE, 4
-    assert L.b200icp_nn_batch(ctypes.byref(pr), 7, ctypes.c_void_p(4096), None, None) == 1
+    assert L.b200icp_nn_batch(ctypes.byref(pr), 7, ctypes.c_void_p(4096), None, 0, None) == 1
     assert L.b200icp_align_batch(ctypes.byref(pr), 1, None, None, None) == 1
-    assert L.b200icp_polar_to_cartesian(None, None, 1, 1, None, None, 1, None) == 1
+    assert L.b200icp_polar_to_cartesian(None, None, 1, 1, None, None, None, 1, None) == 1
+    assert L.b200icp_s2m_search(None, None, None, None, 1, None, None, 1, 0, None, None, None) == 1
+    assert L.b200icp_s2m_inbox_bytes(8192, 8) == 2 * 8 * 8192 * 32 + 17 * 8 and L.b200icp_s2m_inbox_bytes(8, 99) == -1
+    assert L.b200icp_s2m_padded_chunks(1) == 32 and L.b200icp_s2m_padded_chunks(32 * 1024 + 1) == 64
 
 
 def test_no_cpu_fallback(pkg):

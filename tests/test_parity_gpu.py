@@ -68,11 +68,11 @@ def _check_pair(res, p, o, n, *, history=True, rot=TIGHT_ROT, trans=TIGHT_TRANS)
 # ---------------------------------------------------------------------------------------
 # nearest-neighbour kernel (icp.py:37-38)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("nn_block", ["0", "1"])
-def test_nn_first_iteration_all_scan_pairs_bit_exact(b200, cart_scans, monkeypatch, nn_block):
-    monkeypatch.setenv("B200ICP_NN_BLOCK", nn_block)          # warp-per-pair and CTA-per-pair search kernels
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_nn_first_iteration_all_scan_pairs_bit_exact(b200, cart_scans, kernel):
+    """warp-per-pair and CTA-per-pair search kernels"""
     table = b200.ScanTable.from_list(cart_scans)
-    idx, d2 = b200.nn_search(table.slice_rows(1), table.slice_rows(0, table.rows - 1))
+    idx, d2 = b200.nn_search(table.slice_rows(1), table.slice_rows(0, table.rows - 1), kernel=kernel)
     idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
     queries = 0
     for p in range(len(cart_scans) - 1):
@@ -104,12 +104,9 @@ def test_nn_near_ties_and_exact_ties(b200):
         assert np.array_equal(idx[0, :len(src)].cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("nn_variant", [{}, {"B200ICP_NN_BLOCK": "0"}, {"B200ICP_NN_BLOCK": "0", "B200ICP_PRUNE": "0"},
-                                        {"B200ICP_NN_BLOCK": "1"},
-                                        {"B200ICP_NN_BLOCK": "1", "B200ICP_SEARCH_DIRECT": "1"}])
-def test_nn_shapes_ragged_and_limits(b200, monkeypatch, nn_variant):
-    for k, v in nn_variant.items():
-        monkeypatch.setenv(k, v)
+@pytest.mark.parametrize("nn_variant", [{}, {"kernel": "warp"}, {"kernel": "warp", "dense_sweep": True},
+                                        {"kernel": "cta"}])
+def test_nn_shapes_ragged_and_limits(b200, nn_variant):
     rng = np.random.default_rng(11)
     cases = [(1, 1), (1, 7), (5, 1), (31, 33), (32, 8), (33, 9), (129, 257), (385, 77),
              (513, 1025), (1024, 4096), (1000, 4095)]
@@ -119,7 +116,7 @@ def test_nn_shapes_ragged_and_limits(b200, monkeypatch, nn_variant):
         for dt in (np.float64, np.float32):
             s = b200.ScanTable.from_list([A], dtype=dt)
             t = b200.ScanTable.from_list([B], dtype=dt)
-            idx, d2 = b200.nn_search(s, t)
+            idx, d2 = b200.nn_search(s, t, **nn_variant)
             dist, ref = orc.nn_bruteforce(A.astype(dt), B.astype(dt))
             assert np.array_equal(idx[0].cpu().numpy(), ref), (n, m, dt)
             assert np.allclose(np.sqrt(d2[0].cpu().numpy()), dist, rtol=1e-14)
@@ -321,6 +318,21 @@ def test_polar_to_cartesian_device(b200, raw_scans, cart_scans):
     assert exact / total > 0.5
 
 
+@pytest.mark.parametrize("variant", ["slam_offline", "realtime_2", "realtime_1"])
+def test_polar_to_cartesian_reference_variants(b200, raw_scans, variant):
+    """The reference's other copies of polar_to_cartesian_3d (slam_offline.py:62-75, realtime_2.py:153-165,
+    realtime_1.py:160-169) differ in constants only; the device filter takes them as parameters."""
+    sel = raw_scans[::37]
+    table = b200.scan_io.prepare_scans(sel, filter=variant)
+    lens, pts = table.lengths.cpu().numpy(), table.points.cpu().numpy()
+    canon = b200.scan_io.prepare_scans(sel).lengths.cpu().numpy()
+    for k, r in enumerate(sel):
+        ref = orc.polar_to_cartesian_variant(r, variant)
+        assert lens[k] == len(ref)
+        assert np.allclose(pts[k, :len(ref)], ref[:, :2], rtol=0, atol=1e-9)
+    assert int(lens.sum()) > int(canon.sum())               # these variants keep more points than the canonical one
+
+
 def test_reference_shaped_wrappers(b200, cart_scans):
     A, B = cart_scans[3], cart_scans[2]
     d, i = b200.nearest_neighbors(A, B)
@@ -342,23 +354,22 @@ def test_reference_shaped_wrappers(b200, cart_scans):
 # ---------------------------------------------------------------------------------------
 _VARIANTS = {
     "auto": {},
-    "warp-pruned": {"B200ICP_ALIGN_BLOCK": "0"},
-    "warp-pruned-S1": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE_S": "1"},
-    "warp-pruned-S4": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE_S": "4"},
-    "warp-dense": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE": "0"},
-    "warp-pruned-no-reuse": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_REUSE": "0"},
-    "warp-dense-no-reuse": {"B200ICP_ALIGN_BLOCK": "0", "B200ICP_PRUNE": "0", "B200ICP_REUSE": "0"},
-    "block-expanded": {"B200ICP_ALIGN_BLOCK": "1"},
-    "block-direct": {"B200ICP_ALIGN_BLOCK": "1", "B200ICP_SEARCH_DIRECT": "1"},
+    "pair-pruned": {"kernel": "warp"},
+    "pair-pruned-W1": {"kernel": "warp", "pair_warps": 1},
+    "pair-pruned-W3": {"kernel": "warp", "pair_warps": 3},
+    "pair-pruned-W4": {"kernel": "warp", "pair_warps": 4},
+    "pair-dense": {"kernel": "warp", "dense_sweep": True},
+    "pair-pruned-no-reuse": {"kernel": "warp", "sweep_reuse": False},
+    "pair-dense-no-reuse": {"kernel": "warp", "dense_sweep": True, "sweep_reuse": False},
+    "cta": {"kernel": "cta"},
 }
 
 
 @pytest.mark.parametrize("variant", list(_VARIANTS))
-def test_align_variants_on_adversarial_shapes(b200, monkeypatch, variant, cart_scans):
+def test_align_variants_on_adversarial_shapes(b200, variant, cart_scans):
     """Unordered clouds (nothing to prune), far-apart scans (stage A of the pruned sweep hits
     nothing), multi-word group masks (M > 256, > 512), tiny and maximal shapes, duplicates."""
-    for k, v in _VARIANTS[variant].items():
-        monkeypatch.setenv(k, v)
+    kw = _VARIANTS[variant]
     rng = np.random.default_rng(42)
     A, B = [], []
 
@@ -377,7 +388,15 @@ def test_align_variants_on_adversarial_shapes(b200, monkeypatch, variant, cart_s
     add(dup[:40] + rng.normal(0, 0.5, (40, 2)), np.concatenate([dup, dup, dup]))   # exact duplicate targets
     s, t = b200.ScanTable.from_list(A), b200.ScanTable.from_list(B)
     res = b200.align_pairs(s, t, max_iterations=12, tolerance=1e-5, want_history=True, want_src=True,
-                           want_indices=True)
+                           want_indices=True, **kw)
+    if "kernel" in kw:          # the same run without per-point outputs (the LEAN instantiation for float32
+        lean = b200.align_pairs(s, t, max_iterations=12, tolerance=1e-5, **kw)       # tables) gives the same bits
+        assert torch.equal(lean.pose_total, res.pose_total) and torch.equal(lean.iterations, res.iterations)
+        s32, t32 = b200.ScanTable.from_list(A, dtype=np.float32), b200.ScanTable.from_list(B, dtype=np.float32)
+        a32 = b200.align_pairs(s32, t32, max_iterations=12, tolerance=1e-5, want_history=True, **kw)
+        l32 = b200.align_pairs(s32, t32, max_iterations=12, tolerance=1e-5, **kw)
+        assert torch.equal(l32.pose_total, a32.pose_total) and torch.equal(l32.error, a32.error)
+        assert torch.equal(l32.iterations, a32.iterations)
     hist = res.index_history.cpu().numpy()
     for p in range(len(A)):
         o = orc.icp_extended(A[p], B[p], 12, 1e-5, nn="brute", solver="closed")
@@ -453,6 +472,75 @@ def test_host_pipeline_matches_resident_path(b200, cart_scans):
     assert torch.equal(pose2, ref.pose_total.cpu())
 
 
+def test_host_pipeline_back_to_back_runs_do_not_race(b200):
+    """Two run() calls with DIFFERENT inputs and no synchronisation in between: the second run's
+    first copies must not land in staging buffers the first run's kernels are still reading."""
+    n = 6000
+    s1, t1 = orc.synth_room_batch(100, n)
+    s2, t2 = orc.synth_room_batch(50000, n)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h = [pin(s1), pin(t1), pin(s2), pin(t2)]
+    pipe = b200.registration.HostPipeline(n, 360, 360, dtype=torch.float32, chunks=4)
+    for rep in range(3):
+        pa, _, _ = pipe.run(h[0], h[1], max_iterations=30, tolerance=-1.0)
+        if rep == 0:                                        # keep the first run's result once (needs a sync)
+            pipe.done_event.synchronize()
+            first = pa.clone()
+        pb, _, ib = pipe.run(h[2], h[3], max_iterations=30, tolerance=-1.0)
+        pipe.done_event.synchronize()
+        second = pb.clone()
+        ref2 = b200.align_pairs(b200.ScanTable(h[2].cuda()), b200.ScanTable(h[3].cuda()), max_iterations=30,
+                                tolerance=-1.0, kernel="warp")
+        assert torch.equal(second, ref2.pose_total.cpu()), f"repetition {rep}: second run corrupted"
+    ref1 = b200.align_pairs(b200.ScanTable(h[0].cuda()), b200.ScanTable(h[1].cuda()), max_iterations=30,
+                            tolerance=-1.0, kernel="warp")
+    assert torch.equal(first, ref1.pose_total.cpu())
+    with pytest.raises(ValueError):
+        pipe.run(h[0], h[1], torch.zeros(n, dtype=torch.int32).pin_memory(), None)      # one length array only
+    with pytest.raises(ValueError):
+        pipe.run(torch.from_numpy(s1), h[1])                                             # not pinned
+
+
+@pytest.mark.parametrize("tol", [-1.0, 1e-5])
+def test_benchmark_batch_sample_full_history_vs_oracle(b200, tol):
+    """512 pairs drawn from the actual 65,536-pair benchmark batch (bench.py: synth_room_batch(0, 65536)):
+    every iteration's correspondence vector, the iteration count, pose and error against the oracle,
+    through the throughput kernel, for the forced-30 and the tolerance-1e-5 runs."""
+    rng = np.random.default_rng(7)
+    picks = np.sort(rng.choice(65536, size=512, replace=False))
+    src = np.concatenate([orc.synth_room_batch(int(q), 1)[0] for q in picks])
+    tgt = np.concatenate([orc.synth_room_batch(int(q), 1)[1] for q in picks])
+    s, t = b200.ScanTable(torch.from_numpy(src).cuda()), b200.ScanTable(torch.from_numpy(tgt).cuda())
+    res = b200.align_pairs(s, t, max_iterations=30, tolerance=tol, kernel="warp", want_history=True, want_indices=True)
+    lean = b200.align_pairs(s, t, max_iterations=30, tolerance=tol, kernel="warp")
+    assert torch.equal(lean.pose_total, res.pose_total) and torch.equal(lean.iterations, res.iterations)
+    for p in range(len(picks)):
+        o = orc.icp_extended(src[p], tgt[p], 30, tol)
+        _check_pair(res, p, o, 360)
+
+
+def test_triangle_pairing_trajectory_scans_vs_oracle(b200):
+    """configs[3] shape: synth_trajectory_scans (256 rows), pairing='triangle' with a mid-range
+    first_pair (a shard that starts inside a row of the triangle), against the oracle pair by pair."""
+    rows = 256
+    scans = orc.synth_trajectory_scans(rows)
+    table = b200.ScanTable(torch.from_numpy(scans).cuda())
+    first, count = 12345, 300
+    res = b200.align_pairs(table, table, pairing="triangle", first_pair=first, n_pairs=count, max_iterations=30,
+                           tolerance=1e-5, kernel="warp", want_history=True, want_indices=True)
+    for q in range(count):
+        i, j = b200.triangle_pair(first + q, rows)
+        assert 0 <= i < j < rows
+        o = orc.icp_extended(scans[j], scans[i], 30, 1e-5)
+        _check_pair(res, q, o, 360)
+    last = b200.triangle_pair_count(rows) - 5            # the tail of the enumeration
+    tail = b200.align_pairs(table, table, pairing="triangle", first_pair=last, n_pairs=5, max_iterations=30,
+                            tolerance=-1.0, kernel="warp", want_history=True)
+    for q in range(5):
+        i, j = b200.triangle_pair(last + q, rows)
+        _check_pair(tail, q, orc.icp_extended(scans[j], scans[i], 30, -1.0), 360)
+
+
 def test_dense_sweep_flag_gives_identical_bits(b200, cart_scans):
     table = b200.ScanTable.from_list(cart_scans[900:964])
     a = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5, want_indices=True, want_stats=True)
@@ -517,12 +605,11 @@ def test_icp_drop_in_handles_large_sets(b200):
     assert abs(g.fitness - og.fitness) < 1e-12
 
 
-@pytest.mark.parametrize("nn_block", ["0", "1"])
-def test_nn_randomised_stress_exact_indices(b200, monkeypatch, nn_block):
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_nn_randomised_stress_exact_indices(b200, kernel):
     """2,400 random ragged problems: clustered, lattice (exact ties -> lowest index), collinear,
     duplicated, huge offsets (1e6) and tiny scales (1e-3): the pruned FP32 sweep + float64
     re-decision must equal the float64 brute-force argmin everywhere."""
-    monkeypatch.setenv("B200ICP_NN_BLOCK", nn_block)
     rng = np.random.default_rng(2024)
     A, B = [], []
     for q in range(2400):
@@ -549,7 +636,7 @@ def test_nn_randomised_stress_exact_indices(b200, monkeypatch, nn_block):
         A.append(a * scale + off); B.append(b * scale + off)
     for dt in (np.float64, np.float32):
         s, t = b200.ScanTable.from_list(A, dtype=dt), b200.ScanTable.from_list(B, dtype=dt)
-        idx, d2 = b200.nn_search(s, t)
+        idx, d2 = b200.nn_search(s, t, kernel=kernel)
         idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
         hs, ht = s.points.cpu().numpy().astype(np.float64), t.points.cpu().numpy().astype(np.float64)
         for q in range(len(A)):

@@ -30,12 +30,13 @@ def main():
     shard = m.MapShard(torch.from_numpy(full[b:e]).to(dev), global_offset=b)
     scan = torch.from_numpy(scan_np).to(dev)
     o = orc.icp_extended(scan_np, full, iters, -1.0) if rank == 0 else None
-    o_tol = orc.icp_extended(scan_np, full, 30, 1e-3) if rank == 0 else None
+    o_tol = orc.icp_extended(scan_np, full, 30, 0.5) if rank == 0 else None
     ok_all = True
     for exchange, graph in (("peer", False), ("peer", True), ("nccl", False)):
         s2m = m.ScanToMap(shard, N, want_indices=True, exchange=exchange, graph=graph)
         for rep in range(3):                                                   # buffers / graph are reusable
             res = s2m.run(scan, max_iterations=iters, tolerance=-1.0)
+        last_idx = res.indices.clone()
         state = s2m.state.clone()
         gathered = [torch.empty_like(state) for _ in range(world)]
         dist.all_gather(gathered, state)
@@ -43,18 +44,19 @@ def main():
         src_all = [torch.empty_like(s2m.src64) for _ in range(world)]
         dist.all_gather(src_all, s2m.src64)
         same_src = all(torch.equal(g.view(torch.int64), src_all[0].view(torch.int64)) for g in src_all)
-        res_tol = s2m.run(scan, max_iterations=30, tolerance=1e-3)             # early stop: same decision everywhere
+        res_tol = s2m.run(scan, max_iterations=30, tolerance=0.5)              # early stop: same decision everywhere
         its = torch.tensor([res_tol.iterations], device=dev)
         its_all = [torch.empty_like(its) for _ in range(world)]
         dist.all_gather(its_all, its)
         same_its = len({int(t) for t in its_all}) == 1
         if rank == 0:
-            ok_idx = np.array_equal(res.indices.cpu().numpy(), o.indices[-1])
+            ok_idx = np.array_equal(last_idx.cpu().numpy(), o.indices[-1])
             dR = float(np.max(np.abs(res.R - o.R_tot)))
             dt = float(np.max(np.abs(res.t - o.t_tot)))
             de = abs(res.error - o.error)
             ok = (same and same_src and same_its and ok_idx and dR < 1e-9 and dt < 1e-6 and de < 1e-9 and
-                  res.iterations == iters and res_tol.iterations == o_tol.iterations)
+                  res.iterations == iters and res_tol.iterations == o_tol.iterations and
+                  np.array_equal(res_tol.indices.cpu().numpy(), o_tol.indices[-1]))
             ok_all &= ok
             print(f"exchange={exchange} graph={graph} world={world}: state bit-identical across ranks {same}, src64 "
                   f"bit-identical {same_src}, same stop decision {same_its} ({res_tol.iterations} iterations, oracle "

@@ -34,14 +34,11 @@ def main():
         t = m.ScanTable(torch.from_numpy(tgt[None]).cuda())
         out = m.alloc_outputs(1, s.pitch, "cuda")
         kw = dict(n_pairs=1, max_iterations=50, tolerance=1e-5, max_corr_dist=180.0, out=out)
-        os.environ["B200ICP_ALIGN_BLOCK"] = "0"
-        w = timed(lambda: m.align_pairs(s, t, **kw))
+        w = timed(lambda: m.align_pairs(s, t, kernel="warp", **kw))
         its = int(out.iterations[0].item())
         pw = out.pose_total.clone()
-        os.environ["B200ICP_ALIGN_BLOCK"] = "1"
-        b = timed(lambda: m.align_pairs(s, t, **kw))
+        b = timed(lambda: m.align_pairs(s, t, kernel="cta", **kw))
         same = bool(torch.allclose(pw, out.pose_total, atol=1e-9))
-        os.environ["B200ICP_ALIGN_BLOCK"] = "0"
         shard = m.MapShard(torch.from_numpy(tgt).cuda())
         s2m = m.ScanToMap(shard, len(scan), local_only=True)
         sc = torch.from_numpy(scan).cuda()
@@ -58,11 +55,8 @@ def batches():
         s, t = m.ScanTable(S[:P].contiguous()), m.ScanTable(T[:P].contiguous())
         out = m.alloc_outputs(P, 360, "cuda")
         kw = dict(n_pairs=P, max_iterations=30, tolerance=1e-5, out=out)
-        os.environ["B200ICP_ALIGN_BLOCK"] = "0"
-        w = timed(lambda: m.align_pairs(s, t, **kw), reps=10)
-        os.environ["B200ICP_ALIGN_BLOCK"] = "1"
-        b = timed(lambda: m.align_pairs(s, t, **kw), reps=10)
-        os.environ["B200ICP_ALIGN_BLOCK"] = "0"
+        w = timed(lambda: m.align_pairs(s, t, kernel="warp", **kw), reps=10)
+        b = timed(lambda: m.align_pairs(s, t, kernel="cta", **kw), reps=10)
         print(f"{P} pairs 360 x 360: warp kernel {w:.3f} ms, CTA kernel {b:.3f} ms")
 
 

@@ -18,14 +18,13 @@ for name, shuffle in (("ordered", False), ("shuffled", True)):
     S = m.ScanTable(torch.from_numpy(s).cuda().repeat(P // 256, 1, 1))
     T = m.ScanTable(torch.from_numpy(t).cuda().repeat(P // 256, 1, 1))
     for mode in ("1", "0"):
-        os.environ["B200ICP_PRUNE"] = mode
         out = m.alloc_outputs(P, 360, "cuda", want_stats=True)
         for _ in range(2):
-            m.align_pairs(S, T, max_iterations=30, tolerance=-1.0, out=out)
+            m.align_pairs(S, T, max_iterations=30, tolerance=-1.0, dense_sweep=mode == "0", out=out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            m.align_pairs(S, T, max_iterations=30, tolerance=-1.0, out=out)
+            m.align_pairs(S, T, max_iterations=30, tolerance=-1.0, dense_sweep=mode == "0", out=out)
         e1.record(); torch.cuda.synchronize()
         frac = float(out.evaluated_pairs.sum().item()) / (P * 360 * 360 * 30)
         print(f"{name:9s} prune={mode}: {e0.elapsed_time(e1) / 3:7.3f} ms per {P} pairs, executed fraction {frac:.3f}")
