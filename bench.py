@@ -88,6 +88,11 @@ def _cpu_worker(job):
     kind, first, count, tol = job
     from oracle import icp_oracle as orc
     icp, _, _ = reference_icp()
+    try:                                    # one BLAS/OpenMP thread per worker process: the pool is the parallelism
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
     if kind == "rooms":
         src, tgt = orc.synth_room_batch(first, count)
         pairs = [(src[p].astype(np.float64), tgt[p].astype(np.float64)) for p in range(count)]
@@ -370,8 +375,22 @@ def run_b200(args):
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         assert torch.equal(hp, out.pose_total.cpu()), "e2e results differ from the resident-input run"
         h2d, d2h = pipe.bytes_per_run(ragged=False)
+        # the floor of any end-to-end number: the same tables host -> device and nothing else, all ranks at once
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record()
+        for _ in range(3):
+            src.points.copy_(h_src, non_blocking=True)
+            tgt.points.copy_(h_tgt, non_blocking=True)
+        c1.record()
+        barrier()
+        h2d_ms = max_over_ranks(c0.elapsed_time(c1)) / 3
         e2e = {"value": world * P / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "launches_per_step": pipe.launches,
+               "h2d_only_ms": h2d_ms, "h2d_only_gbs_per_gpu": h2d / (h2d_ms * 1e-3) / 1e9,
+               "limiter": ("host-to-device copy" if h2d_ms > 0.9 * e2e_ms else "kernel") +
+                          ": e2e = max(kernel, copy) + the first chunk's copy; h2d_only_ms is the copy alone with every "
+                          "rank copying at once (GPUs share host memory and PCIe uplinks)",
                "api": "icp_slam_yolo_b200.registration.HostPipeline.run (%d chunks, copy/compute overlap)" % n_chunks}
         del pipe
 

@@ -1583,14 +1583,37 @@ __global__ void __launch_bounds__(256) select_count_kernel(const void* points, i
   }
 }
 
-// exclusive scan of the per-block counts in place; total -> counts[n_blocks] and *count_out
-__global__ void select_scan_kernel(int64_t* counts, int64_t n_blocks, int64_t* count_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int64_t run = 0;
-    for (int64_t b = 0; b < n_blocks; ++b) { const int64_t c = counts[b]; counts[b] = run; run += c; }
-    counts[n_blocks] = run;
-    *count_out = run;
+// exclusive scan of the per-block counts in place (one CTA: every thread owns a contiguous
+// segment, warp-shuffle scan of the segment sums); total -> counts[n_blocks] and *count_out
+__global__ void __launch_bounds__(1024) select_scan_kernel(int64_t* counts, int64_t n_blocks, int64_t* count_out) {
+  __shared__ long long wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (n_blocks + 1023) / 1024;
+  const int64_t b = min(n_blocks, tid * per), e = min(n_blocks, b + per);
+  long long s = 0;
+  for (int64_t k = b; k < e; ++k) s += counts[k];
+  long long inc = s;                                   // inclusive scan inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long v = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += v;
   }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {                                     // exclusive scan of the 32 warp totals
+    const long long w = wsum[lane];
+    long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(kFull, winc, o);
+      if (lane >= o) winc += v;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  long long run = wsum[warp] + inc - s;
+  for (int64_t k = b; k < e; ++k) { const long long c = counts[k]; counts[k] = run; run += c; }
+  if (tid == 1023) { counts[n_blocks] = run; *count_out = run; }
 }
 
 __global__ void __launch_bounds__(256) select_scatter_kernel(const void* points, int dtype, int64_t n,
@@ -1658,19 +1681,47 @@ __global__ void __launch_bounds__(1024) chain_poses_kernel(const double* __restr
   const int64_t b = min(n, tid * per), e = min(n, b + per);
   Se2 acc = se2_identity();
   for (int64_t k = b; k < e; ++k) acc = se2_mul(acc, se2_load(poses + 6 * k));
-  se2_store(seg[tid], acc);
-  __syncthreads();
-  if (tid == 0) {                       // exclusive scan of the segment totals
-    Se2 run = se2_identity();
-    for (int q = 0; q < 1024; ++q) {
-      const Se2 t = se2_load(seg[q]);
-      se2_store(seg[q], run);
-      run = se2_mul(run, t);
-    }
-    se2_store(out, se2_identity());
+  // exclusive scan of the 1,024 segment totals: composition is associative, so a shuffle scan
+  // inside every warp and one over the 32 warp totals replace the serial loop (order of the
+  // factors preserved: earlier segments on the left)
+  const int lane = tid & 31, warp = tid >> 5;
+  Se2 inc = acc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Se2 v;
+    v.r00 = __shfl_up_sync(kFull, inc.r00, o); v.r01 = __shfl_up_sync(kFull, inc.r01, o);
+    v.r10 = __shfl_up_sync(kFull, inc.r10, o); v.r11 = __shfl_up_sync(kFull, inc.r11, o);
+    v.tx = __shfl_up_sync(kFull, inc.tx, o); v.ty = __shfl_up_sync(kFull, inc.ty, o);
+    if (lane >= o) inc = se2_mul(v, inc);
   }
+  Se2 excl = inc;                        // exclusive within the warp: the neighbour's inclusive value
+  excl.r00 = __shfl_up_sync(kFull, inc.r00, 1); excl.r01 = __shfl_up_sync(kFull, inc.r01, 1);
+  excl.r10 = __shfl_up_sync(kFull, inc.r10, 1); excl.r11 = __shfl_up_sync(kFull, inc.r11, 1);
+  excl.tx = __shfl_up_sync(kFull, inc.tx, 1); excl.ty = __shfl_up_sync(kFull, inc.ty, 1);
+  if (lane == 0) excl = se2_identity();
+  if (lane == 31) se2_store(seg[warp], inc);           // warp totals in seg[0..31]
   __syncthreads();
-  acc = se2_load(seg[tid]);
+  if (warp == 0) {
+    const Se2 w = se2_load(seg[lane]);
+    Se2 winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Se2 v;
+      v.r00 = __shfl_up_sync(kFull, winc.r00, o); v.r01 = __shfl_up_sync(kFull, winc.r01, o);
+      v.r10 = __shfl_up_sync(kFull, winc.r10, o); v.r11 = __shfl_up_sync(kFull, winc.r11, o);
+      v.tx = __shfl_up_sync(kFull, winc.tx, o); v.ty = __shfl_up_sync(kFull, winc.ty, o);
+      if (lane >= o) winc = se2_mul(v, winc);
+    }
+    Se2 wex;
+    wex.r00 = __shfl_up_sync(kFull, winc.r00, 1); wex.r01 = __shfl_up_sync(kFull, winc.r01, 1);
+    wex.r10 = __shfl_up_sync(kFull, winc.r10, 1); wex.r11 = __shfl_up_sync(kFull, winc.r11, 1);
+    wex.tx = __shfl_up_sync(kFull, winc.tx, 1); wex.ty = __shfl_up_sync(kFull, winc.ty, 1);
+    if (lane == 0) wex = se2_identity();
+    se2_store(seg[32 + lane], wex);                    // exclusive warp prefixes in seg[32..63]
+  }
+  if (tid == 0) se2_store(out, se2_identity());
+  __syncthreads();
+  acc = se2_mul(se2_load(seg[32 + warp]), excl);
   for (int64_t k = b; k < e; ++k) {
     acc = se2_mul(acc, se2_load(poses + 6 * k));
     se2_store(out + 6 * (k + 1), acc);
@@ -1978,7 +2029,7 @@ int b200icp_select_points(const void* points, int32_t dtype, int64_t n, int32_t 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "select_count_kernel");
   }
-  select_scan_kernel<<<1, 32, 0, st>>>(scratch, blocks, count_out);
+  select_scan_kernel<<<1, 1024, 0, st>>>(scratch, blocks, count_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "select_scan_kernel");
   if (blocks > 0) {

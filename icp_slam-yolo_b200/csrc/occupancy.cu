@@ -644,12 +644,37 @@ __global__ void __launch_bounds__(256) occ_filter_count_kernel(const T* points, 
   }
 }
 
-__global__ void occ_filter_scan_kernel(int64_t* counts, int64_t n_blocks, int64_t* count_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int64_t run = 0;
-    for (int64_t b = 0; b < n_blocks; ++b) { const int64_t c = counts[b]; counts[b] = run; run += c; }
-    *count_out = run;
+// exclusive scan of the per-block counts in place (one CTA; see select_scan_kernel in b200icp.cu)
+__global__ void __launch_bounds__(1024) occ_filter_scan_kernel(int64_t* counts, int64_t n_blocks, int64_t* count_out) {
+  __shared__ long long wsum[32];
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (n_blocks + 1023) / 1024;
+  const int64_t b = min(n_blocks, tid * per), e = min(n_blocks, b + per);
+  long long s = 0;
+  for (int64_t k = b; k < e; ++k) s += counts[k];
+  long long inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long v = __shfl_up_sync(full, inc, o);
+    if (lane >= o) inc += v;
   }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const long long w = wsum[lane];
+    long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(full, winc, o);
+      if (lane >= o) winc += v;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  long long run = wsum[warp] + inc - s;
+  for (int64_t k = b; k < e; ++k) { const long long c = counts[k]; counts[k] = run; run += c; }
+  if (tid == 1023) *count_out = run;
 }
 
 template <typename T>
@@ -755,7 +780,7 @@ int b200icp_occ_filter_points(const void* points, int32_t dtype, int32_t cols, i
     e = cudaGetLastError();
     if (e != cudaSuccess) { occ_fail(e, "occ_filter_count_kernel"); return B200ICP_ERR_CUDA; }
   }
-  occ_filter_scan_kernel<<<1, 32, 0, st>>>(scratch, blocks, count_out);
+  occ_filter_scan_kernel<<<1, 1024, 0, st>>>(scratch, blocks, count_out);
   e = cudaGetLastError();
   if (e != cudaSuccess) { occ_fail(e, "occ_filter_scan_kernel"); return B200ICP_ERR_CUDA; }
   if (blocks > 0) {

@@ -76,14 +76,27 @@ __global__ void __launch_bounds__(1024) voxel_scan_kernel(const int32_t* flag, i
   const int64_t per = (n + 1023) / 1024, b = min(n, tid * per), e = min(n, b + per);
   int32_t s = 0;
   for (int64_t k = b; k < e; ++k) s += flag[k];
-  tot[tid] = s;
+  const int lane = tid & 31, warp = tid >> 5;
+  int32_t inc = s;                                      // warp-shuffle scan of the segment sums
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) tot[warp] = inc;
   __syncthreads();
-  if (tid == 0) {
-    int32_t run = 0;
-    for (int q = 0; q < 1024; ++q) { const int32_t v = tot[q]; tot[q] = run; run += v; }
+  if (warp == 0) {
+    const int32_t w = tot[lane];
+    int32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    tot[lane] = winc - w;
   }
   __syncthreads();
-  int32_t run = tot[tid];
+  int32_t run = tot[warp] + inc - s;
   for (int64_t k = b; k < e; ++k) { run += flag[k]; rank[k] = run - 1; }
 }
 

@@ -51,6 +51,13 @@ def _worker(rank, world, port, out_dir):
     lo, hi = m.shard_range(len(map_pts), rank, world)
     dloc, iloc = orc.nn_bruteforce(scan, map_pts[lo:hi])
     rec = np.stack([dloc ** 2, (iloc + lo).astype(np.float64), map_pts[lo:hi][iloc, 0], map_pts[lo:hi][iloc, 1]], axis=1)
+    # round-2 protocol: a rank answers "none" (+inf) for every point whose nearest neighbour provably
+    # lies in another shard, i.e. whose local best is farther than a bound of the GLOBAL distance
+    # (device: bounding circles of all ranks' chunks; here: the min over ranks of the local bests)
+    ub = torch.from_numpy(dloc.copy())
+    dist.all_reduce(ub, op=dist.ReduceOp.MIN)
+    none = dloc > ub.numpy()
+    rec[none] = [np.inf, float(np.iinfo(np.int64).max), 0.0, 0.0]
     rec_all = torch.zeros((world * len(scan), 4), dtype=torch.float64)    # rank-major, like NCCL
     dist.all_gather_into_tensor(rec_all, torch.from_numpy(rec))
     ra = rec_all.numpy().reshape(world, len(scan), 4)
