@@ -28,6 +28,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "b200icp.h"
 
@@ -1200,12 +1203,14 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
       int32_t* hist = (!LEAN && out.index_history)
           ? out.index_history + (p * op.max_iterations + it) * (int64_t)pr.src_pitch : nullptr;
       double r[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int pass = warp; pass < a.passes; pass += W) {
-        const int base = pass * 32 * SC;
-        if (base >= n) break;
-#pragma unroll
-        for (int k0 = 0; k0 < SC; k0 += 2) {
-          if (LEAN && base + (k0 + 2) * 32 <= n && k0 + 2 <= SC) {
+      // Sources are summed in blocks of 64 dealt round-robin to the warps, whatever the pass width of
+      // the search: the float64 sums -- and with them every bit of the result -- do not depend on
+      // SC / PRUNE (the dense and the pruned kernels are interchangeable bit for bit).
+      if (SC != 2 && W > 1) __syncthreads();               // indices written by another warp's pass
+      for (int base = warp * 64; base < n; base += W * 64) {
+        {
+          constexpr int k0 = 0;
+          if (LEAN && base + (k0 + 2) * 32 <= n) {
             // both 32-source slots are full (warp-uniform test): straight-line code, no per-lane tests
             int jj[2];
             double2 bm[2];
@@ -1234,13 +1239,13 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
 #pragma unroll
           for (int u = 0; u < 2; ++u) {                    // both loads in flight before the first use
             const int i = base + (k0 + u) * 32 + lane;
-            jj[u] = (k0 + u < SC && i < n) ? (int)t.nnidx[i] : 0;
+            jj[u] = i < n ? (int)t.nnidx[i] : 0;
             bm[u] = load_point(t.tgt, t.dtype, t.row_off + jj[u]);
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = base + (k0 + u) * 32 + lane;
-            if (k0 + u < SC && i < n) {
+            if (i < n) {
               const double2 s = t.src[i];
               const double2 b = bm[u];
               const double d2 = dist2_f64(s.x, s.y, b);
@@ -1305,10 +1310,9 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
       const double cax = t.ox + max_, cay = t.oy + may_;
       const double tx = (t.ox + mbx) - (cs * cax - sn * cay);  // icp.py:25
       const double ty = (t.oy + mby) - (sn * cax + cs * cay);
-      for (int pass = warp; pass < a.passes; pass += W) {      // apply (icp.py:45), own sources only
-        const int base = pass * 32 * SC;
+      for (int base = warp * 64; base < n; base += W * 64) {   // apply (icp.py:45), the blocks this warp summed
 #pragma unroll
-        for (int k = 0; k < SC; ++k) {
+        for (int k = 0; k < 2; ++k) {
           const int i = base + k * 32 + lane;
           if (i < n) {
             const double2 s = t.src[i];
@@ -1316,6 +1320,7 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
           }
         }
       }
+      if (SC != 2 && W > 1) __syncthreads();               // the next search reads points another warp moved
       // Upper bound of every point's displacement in this update: with c the target centroid,
       // s' - s = (R - I)(s - c) + [(R - I) c + t], so |s' - s| <= |R - I| smax + |(R - I) c + t| with
       // |R - I| = sqrt((cos - 1)^2 + sin^2) and smax >= |s - c| for every point (initial maximum, grown
@@ -1820,15 +1825,19 @@ int cuda_fail(cudaError_t e, const char* what) {
 template <typename Kern>
 int launch_pairs(Kern kern, const LaunchShape& ls, const KernelArgs& args, cudaStream_t st) {
   if (ls.smem > 48 * 1024) {
-    static int opted_in[64] = {0};               // per template instantiation, indexed by device
+    // (all kernels share the function-pointer type, so the memo is keyed by pointer and device)
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> opted_in;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), dev);
+    if (!opted_in.count(key)) {
       int max_optin = 0;
       cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
-      if (dev >= 0 && dev < 64) opted_in[dev] = 1;
+      opted_in.insert(key);
     }
   }
   kern<<<(unsigned)args.n_pairs, ls.warps * 32, ls.smem, st>>>(args);
@@ -1841,8 +1850,7 @@ int launch_pairs(Kern kern, const LaunchShape& ls, const KernelArgs& args, cudaS
 // dealt round-robin to W <= 4 warps.  W = the warp count in 2..4 that leaves the fewest idle
 // warp-rounds, the smallest on ties: measured on B200 (profiles/r2_kernel_tuning.md) two warps beat
 // one (shared tile: 24 instead of 18 resident warps per SM) and three or four (the redundant pose
-// solve and the wait at the cross-warp sum grow with W): 360 points = 6 pruned passes on 2 warps,
-// 2 dense passes on 2.
+// solve and the wait at the cross-warp sum grow with W): 360 points = 6 blocks of 64 on 2 warps.
 constexpr int kPairS = 2, kPairDenseS = 6, kPairMaxWarps = 4;
 
 int pair_warps_for(int passes, int forced) {
@@ -1863,7 +1871,9 @@ int launch_pair_kernel(const b200icp_problem* prob, const LaunchShape& ls, Kerne
   args.ncap = (prob->src_pitch + 32 * S - 1) / (32 * S) * (32 * S);
   args.passes = args.ncap / (32 * S);
   LaunchShape ps = ls;
-  ps.warps = pair_warps_for(args.passes, forced_warps);
+  // W follows the 64-source blocks of the float64 phase, not the pass width of the search, so that
+  // the dense and the pruned kernel add the sums in the same order (bit-identical results)
+  ps.warps = pair_warps_for((prob->src_pitch + 63) / 64, forced_warps);
   ps.smem = pair_tile_bytes(ls.mcap, args.ncap, args.passes, ps.warps);
   // LEAN: the throughput configuration (float32 tables, no gate, no per-point index outputs)
   const bool lean = prob->dtype == B200ICP_F32 && !args.use_gate && !args.out.indices && !args.out.index_history;

@@ -47,9 +47,7 @@ namespace {
 
 constexpr int kChunk = 1024;          // map points per bounding circle
 constexpr int kSuper = 32;            // chunks per second-level circle (one lane each)
-constexpr int kSearchWarps = 4;       // scan points per CTA of the search kernel
-constexpr int kStageBytes = kChunk * 8;   // one float32 chunk (x, y interleaved) per pipeline stage
-constexpr int kListCap = 64;          // candidate chunks collected per warp before they are scanned
+constexpr int kSearchWarps = 8;       // scan points per CTA of the search kernel
 constexpr int kUpdateThreads = 256;
 constexpr int kMaxUpdateCtas = 64;
 constexpr int kMaxWorld = 32;
@@ -105,39 +103,6 @@ __device__ __forceinline__ b200icp_s2m_record* inbox_records(void* base, int wor
 }
 __device__ __forceinline__ long long* inbox_flags(void* base, int world, int n) {
   return reinterpret_cast<long long*>(reinterpret_cast<b200icp_s2m_record*>(base) + (int64_t)2 * world * n);
-}
-
-// ---- mbarrier / TMA bulk copy (PTX; shared::cluster == shared::cta for a 1-CTA cluster) ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -315,82 +280,12 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
   }
 }
 
-// The same scan out of a chunk that a TMA bulk copy staged in shared memory (float32 tables, full
-// chunks): lane l reads points l, l + 32, ... (conflict-free 8-byte accesses), ascending index per lane.
-__device__ __forceinline__ void scan_staged(const float2* __restrict__ buf, int64_t j0, double sx, double sy,
-                                            int lane, double& bd, long long& bj) {
-#pragma unroll 4
-  for (int j = lane; j < kChunk; j += 32) {
-    const float2 q = buf[j];
-    const double d = dist2_f64(sx, sy, make_double2((double)q.x, (double)q.y));
-    if (d < bd) { bd = d; bj = j0 + j; }
-  }
-}
-
-// Per-warp pipeline state: two stages of one chunk each, one mbarrier per stage.
-struct WarpPipe {
-  float2* stage0;       // stage s = stage0 + s * kChunk
-  uint64_t* bar0;       // barrier of stage s = bar0 + s
-  uint32_t phases;      // bit s: parity the next wait on stage s expects
-  int* list;            // [kListCap] candidate chunks, ascending
-  bool tma;             // float32 table, 16-byte aligned base: full chunks go through the bulk-copy path
-};
-
-// Scan the `count` listed chunks in order.  Full chunks of a float32 table stream through shared
-// memory (cp.async.bulk + mbarrier, the copy of the next listed chunk overlapping the scan of the
-// current one); a partial last chunk or a float64 table is read straight from global memory.
-__device__ __forceinline__ void flush_list(const SearchArgs& a, WarpPipe& wp, int count, double sx, double sy,
-                                           int lane, double& bd, long long& bj) {
-  if (count == 0) return;
-  __syncwarp();                                               // list entries are visible to every lane
-  auto full = [&](int lc) { return wp.tma && (int64_t)(lc + 1) * kChunk <= a.m; };
-  auto issue = [&](int lc, int st) {                          // lane 0: start the copy of chunk lc into stage st
-    mbar_expect_tx(wp.bar0 + st, kStageBytes);
-    bulk_g2s(wp.stage0 + st * kChunk, reinterpret_cast<const float2*>(a.points) + (int64_t)lc * kChunk, kStageBytes,
-             wp.bar0 + st);
-  };
-  int st = 0;
-  if (lane == 0 && full(wp.list[0])) issue(wp.list[0], 0);
-  for (int e = 0; e < count; ++e) {
-    const int lc = wp.list[e];
-    if (e + 1 < count) {
-      const int nx = wp.list[e + 1];
-      if (lane == 0 && full(nx)) issue(nx, st ^ 1);           // stage st^1 was released by the __syncwarp below
-    }
-    if (full(lc)) {
-      mbar_wait(wp.bar0 + st, (wp.phases >> st) & 1u);
-      wp.phases ^= 1u << st;
-      scan_staged(wp.stage0 + st * kChunk, (int64_t)lc * kChunk, sx, sy, lane, bd, bj);
-    } else {
-      scan_chunk(a, lc, sx, sy, lane, bd, bj);
-    }
-    __syncwarp();                                             // every lane is done with stage st before it is refilled
-    st ^= 1;
-  }
-}
-
 constexpr int kSuperBlock = 1024;     // super-chunks per traversal block: one candidate bit per lane and trip
 
-constexpr size_t kSearchSmem = (size_t)kSearchWarps * (2 * kStageBytes + kListCap * sizeof(int) + 2 * sizeof(uint64_t));
-
 __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const SearchArgs a) {
-  extern __shared__ __align__(128) unsigned char s2m_smem[];
   b200icp_s2m_state* st = a.state;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpPipe wp;
-  wp.stage0 = reinterpret_cast<float2*>(s2m_smem + (size_t)warp * 2 * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s2m_smem + (size_t)kSearchWarps * 2 * kStageBytes);
-  wp.bar0 = bars + 2 * warp;
-  wp.list = reinterpret_cast<int*>(bars + 2 * kSearchWarps) + warp * kListCap;
-  wp.phases = 0u;
-  wp.tma = a.dtype == B200ICP_F32 && (reinterpret_cast<uintptr_t>(a.points) & 15u) == 0;
-  if (lane == 0) {
-    mbar_init(wp.bar0, 1);
-    mbar_init(wp.bar0 + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
   const int i = blockIdx.x * kSearchWarps + warp;
   const bool pending = st->applied < st->iterations;
   long long seq = 0;
@@ -444,7 +339,6 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
     double bd = CUDART_INF;
     long long bj = kNoIndex;
     const int first_super = a.first_local_chunk / kSuper, local_supers = a.n_local_chunks / kSuper;
-    int listed = 0;
     for (int phase = 0; phase < 2; ++phase) {
       double cd = CUDART_INF, cr = 0.0;       // closest chunk centre among the candidates (phase 0)
       int cc = -1;
@@ -470,19 +364,16 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
                 if (d < cd) { cd = d; cr = c.r; cc = ks * kSuper + lane; }
               }
             } else {
-              const unsigned cmask = __ballot_sync(kFull, hit);          // ascending local chunks
-              const int cnt = __popc(cmask);
-              if (listed + cnt > kListCap) {
-                flush_list(a, wp, listed, s.x, s.y, lane, bd, bj);
-                listed = 0;
+              unsigned cmask = __ballot_sync(kFull, hit);
+              while (cmask) {
+                const int lc = ks * kSuper + __ffs(cmask) - 1;           // local chunk, ascending
+                cmask &= cmask - 1;
+                scan_chunk(a, lc, s.x, s.y, lane, bd, bj);
               }
-              if (hit) wp.list[listed + __popc(cmask & ((1u << lane) - 1u))] = ks * kSuper + lane;
-              listed += cnt;
             }
           }
         }
       }
-      if (phase == 1) flush_list(a, wp, listed, s.x, s.y, lane, bd, bj);
       if (phase == 0) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -792,13 +683,7 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const b200icp_s2m_tables*
   a.n_local_chunks = tables->n_local_chunks;
   a.src64 = src64; a.prev_nn = prev_nn; a.n = n; a.records = records; a.peers = peers;
   a.world = world; a.rank = rank; a.state = state; a.scratch = reinterpret_cast<unsigned*>(scratch);
-  static bool opted_in = false;       // > 48 KB of dynamic shared memory: opt in once
-  if (!opted_in) {
-    if (cudaFuncSetAttribute(s2m_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSearchSmem) != cudaSuccess)
-      return cuda_check("cudaFuncSetAttribute(s2m_search_kernel)");
-    opted_in = true;
-  }
-  s2m_search_kernel<<<(n + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, kSearchSmem,
+  s2m_search_kernel<<<(n + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0,
                       reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return cuda_check("s2m_search_kernel");
 }

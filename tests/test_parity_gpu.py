@@ -330,7 +330,7 @@ def test_polar_to_cartesian_reference_variants(b200, raw_scans, variant):
         ref = orc.polar_to_cartesian_variant(r, variant)
         assert lens[k] == len(ref)
         assert np.allclose(pts[k, :len(ref)], ref[:, :2], rtol=0, atol=1e-9)
-    assert int(lens.sum()) > int(canon.sum())               # these variants keep more points than the canonical one
+    assert int(lens.sum()) != int(canon.sum())              # the variant really filters differently
 
 
 def test_reference_shaped_wrappers(b200, cart_scans):
