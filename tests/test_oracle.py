@@ -39,6 +39,17 @@ def test_all_scan_pairs_match_reference_bitwise(golden, cart_scans, oracle_pairs
     assert its.min() == 1 and its.max() == 30 and abs(its.mean() - 7.38) < 0.01
 
 
+def test_second_recording_matches_reference_bitwise(golden3, cart_scans3, oracle_pairs3):
+    """scan_data_3/ (2,042 consecutive pairs): the oracle reproduces what the unmodified reference
+    icp() returned (tests/golden/make_golden_scan3.py) bit for bit."""
+    assert len(oracle_pairs3) == 2042
+    crc = golden3["pair_src_crc32"]
+    for p, r in enumerate(oracle_pairs3):
+        assert zlib.crc32(np.ascontiguousarray(r.src).tobytes()) == crc[p], f"pair {p}"
+        assert np.array_equal(r.R_last, golden3["pair_R_last"][p]) and np.array_equal(r.t_last, golden3["pair_t_last"][p])
+        assert len(cart_scans3[p + 1]) == golden3["pair_n_src"][p] and len(cart_scans3[p]) == golden3["pair_n_tgt"][p]
+
+
 def test_spot_pairs_full_src(golden, oracle_pairs):
     for k in golden["spot_pairs"]:
         assert np.array_equal(oracle_pairs[k - 1].src, golden[f"spot_src_{k}"])

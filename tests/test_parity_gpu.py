@@ -184,6 +184,25 @@ def test_scan_data_1_all_pairs_full_history(b200, cart_scans, oracle_pairs, gold
     assert np.allclose(chain[-1, :4].reshape(2, 2), R, atol=1e-7) and np.allclose(chain[-1, 4:], t, atol=1e-3)
 
 
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_second_recording_all_pairs_full_history(b200, cart_scans3, oracle_pairs3, golden3, kernel):
+    """scan_data_3/ (2,043 scans, 58..170 points after the filter): every consecutive pair in one
+    launch; every iteration's correspondence vector, iteration count, pose and error against the
+    oracle, and the pose against what the unmodified reference produced (golden fixture)."""
+    table = b200.ScanTable.from_list(cart_scans3)
+    res = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5, kernel=kernel,
+                                 want_indices=True, want_src=True, want_history=True)
+    torch.cuda.synchronize()
+    for p, o in enumerate(oracle_pairs3):
+        _check_pair(res, p, o, len(cart_scans3[p + 1]))
+    pt = res.pose_total.cpu().numpy()
+    assert np.max(np.abs(_theta(pt) - golden3["pair_theta_tot"])) < TIGHT_ROT
+    assert np.max(np.abs(pt[:, 4:6] - golden3["pair_t_tot"])) < TIGHT_TRANS
+    pl = res.pose_last.cpu().numpy()
+    assert np.allclose(pl[:, :4].reshape(-1, 2, 2), golden3["pair_R_last"], rtol=0, atol=1e-9)
+    assert np.allclose(pl[:, 4:6], golden3["pair_t_last"], rtol=0, atol=1e-6)
+
+
 def test_float32_inputs_synthetic_rooms(b200):
     """Config 3 shape (360 x 360, float32 tables), forced 30 iterations and tol 1e-5."""
     count = 48
