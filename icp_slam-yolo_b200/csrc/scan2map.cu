@@ -47,7 +47,7 @@ namespace {
 
 constexpr int kChunk = 1024;          // map points per bounding circle
 constexpr int kSuper = 32;            // chunks per second-level circle (one lane each)
-constexpr int kSearchWarps = 8;       // scan points per CTA of the search kernel
+constexpr int kSearchWarps = 8;       // warps per CTA of the search kernel
 constexpr int kUpdateThreads = 256;
 constexpr int kMaxUpdateCtas = 64;
 constexpr int kMaxWorld = 32;
@@ -286,7 +286,11 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
   b200icp_s2m_state* st = a.state;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // One warp per scan point.  (Several warps per point, each scanning every k-th listed chunk, were
+  // measured: the repeated circle traversal costs more than the shorter load chain saves --
+  // profiles/r2_kernel_tuning.md.)
   const int i = blockIdx.x * kSearchWarps + warp;
+  const bool active = i < a.n;
   const bool pending = st->applied < st->iterations;
   long long seq = 0;
   int slot = 0;
@@ -294,7 +298,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
     seq = *(inbox_flags(a.peers[a.rank], a.world, a.n) + 2 * a.world) + 1;   // exchange counter of this rank
     slot = (int)(seq & 1);
   }
-  if (i < a.n) {
+  double bd = CUDART_INF;
+  long long bj = kNoIndex;
+  if (active) {
     double2 s = make_double2(a.src64[2 * i], a.src64[2 * i + 1]);
     if (pending) {
       s = apply_pending(st, s);
@@ -335,9 +341,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
     // ---- (3) exact float64 scan of every local chunk within reach.  Two traversals of the local
     // circles: the first finds the chunk whose centre is closest; if the bound is wider than that
     // chunk (the scan moved a lot, or this is the first iteration) the chunk is scanned first and
-    // its best distance becomes the bound.  The second scans every chunk within the bound.
-    double bd = CUDART_INF;
-    long long bj = kNoIndex;
+    // its best distance becomes the bound.  The second scans every chunk within the bound, ascending.
     const int first_super = a.first_local_chunk / kSuper, local_supers = a.n_local_chunks / kSuper;
     for (int phase = 0; phase < 2; ++phase) {
       double cd = CUDART_INF, cr = 0.0;       // closest chunk centre among the candidates (phase 0)
@@ -396,25 +400,24 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
       const long long oj = __shfl_xor_sync(kFull, bj, o);
       if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
     }
-    if (lane == 0) {
-      b200icp_s2m_record rec;
-      rec.d2 = bd; rec.gidx = kNoIndex; rec.bx = 0.0; rec.by = 0.0;      // "none": the NN is in another shard
-      if (bj != kNoIndex) {
-        const double2 b = load_point(a.points, a.dtype, bj);
-        rec.gidx = a.global_offset + bj; rec.bx = b.x; rec.by = b.y;
-      }
-      if (a.peers) {
-        for (int r = 0; r < a.world; ++r) inbox_records(a.peers[r], a.world, a.n, slot, a.rank)[i] = rec;
-        __threadfence_system();
-      } else {
-        a.records[i] = rec;
-      }
+    b200icp_s2m_record rec;
+    rec.d2 = bd; rec.gidx = kNoIndex; rec.bx = 0.0; rec.by = 0.0;        // "none": the NN is in another shard
+    if (bj != kNoIndex) {
+      const double2 b = load_point(a.points, a.dtype, bj);
+      rec.gidx = a.global_offset + bj; rec.bx = b.x; rec.by = b.y;
+    }
+    if (a.peers) {                                           // lane r stores into rank r's inbox
+      for (int r = lane; r < a.world; r += 32) inbox_records(a.peers[r], a.world, a.n, slot, a.rank)[i] = rec;
+    } else if (lane == 0) {
+      a.records[i] = rec;
     }
   }
-  // ---- (4) last CTA: the pending increment is applied everywhere; raise this rank's flag on every rank
+  // ---- (4) last CTA: the pending increment is applied everywhere; raise this rank's flag on every rank.
+  // One system-scope fence per CTA (after the barrier: cumulative over the stores of all its warps)
+  // orders the records before the ticket, the ticket chain before the last CTA's fence and flag.
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (a.peers) __threadfence_system(); else __threadfence();
     const unsigned ticket = atomicAdd(a.scratch + kTicketSearch, 1u);
     if (ticket == gridDim.x - 1) {
       a.scratch[kTicketSearch] = 0u;
