@@ -78,3 +78,39 @@ def test_scan_to_map_duplicates_resolve_to_lowest_global_index(b200):
     run.step(1, -1.0)
     _, ref = orc.nn_bruteforce(scan, map_pts)
     assert np.array_equal(run.indices.cpu().numpy(), ref) and ref.max() < 3000
+
+
+def test_scan_to_map_cuda_graph_replay_equals_eager(b200):
+    """ScanToMap(graph=True): the whole fixed-length loop captured once and replayed (different
+    scans, same arguments) gives the bits of the eager loop."""
+    map_pts = orc.synth_map(1 << 16)
+    shard = b200.MapShard(torch.from_numpy(map_pts).cuda())
+    eager = b200.ScanToMap(shard, 2048, want_indices=True)
+    graph = b200.ScanToMap(shard, 2048, want_indices=True, graph=True)
+    for seed in (77, 78, 79):
+        scan = torch.from_numpy(orc.synth_scan_for_map(2048, scan_seed=seed)).cuda()
+        for tol in (-1.0, 1e-2):
+            a = eager.run(scan, max_iterations=12, tolerance=tol)
+            ia, sa = a.indices.clone(), a.src.clone()
+            g = graph.run(scan, max_iterations=12, tolerance=tol)
+            assert a.iterations == g.iterations and a.error == g.error
+            assert np.array_equal(a.R, g.R) and np.array_equal(a.t, g.t)
+            assert torch.equal(ia, g.indices) and torch.equal(sa, g.src)
+    o = orc.icp_extended(orc.synth_scan_for_map(2048, scan_seed=79), map_pts, 12, 1e-2)
+    assert g.iterations == o.iterations and np.array_equal(g.indices.cpu().numpy(), o.indices[-1])
+
+
+def test_scan_to_map_float64_map_and_unaligned_sizes(b200):
+    """float64 map (16-byte points: the four-load scan path), shard sizes that leave a partial last
+    chunk and a padded circle table, scan sizes that are not a multiple of the CTA's eight points."""
+    map_pts = orc.synth_map(40000 + 17, dtype=np.float64)
+    scan = orc.synth_scan_for_map(1003, dtype=np.float64)
+    o = orc.icp_extended(scan, map_pts, 5, -1.0)
+    for n_shards in (1, 5):
+        run = b200.scan_to_map.ScanToMapLocalShards(_shards(b200, map_pts, n_shards), len(scan))
+        run.init(torch.from_numpy(scan).cuda())
+        for it in range(5):
+            run.step(5, -1.0)
+            assert np.array_equal(run.indices.cpu().numpy(), o.indices[it]), (n_shards, it)
+        r = run.result()
+        assert np.allclose(r.R, o.R_tot, atol=1e-9) and np.allclose(r.t, o.t_tot, atol=1e-6)
