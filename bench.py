@@ -653,7 +653,7 @@ def run_odometry(args, ctx=None):
                                "tolerance 1e-5, ragged 11..196 points", "iterations_total": gpu_its,
                    "l2": "inputs (5.7 MB) fit L2: a 64 MB buffer is NOT flushed between steps; noted"},
         "gpu_launches": args.steps,
-        "roofline": {"bound": "fp32", "kernel": "icp_align_kernel (CTA per pair: the dispatcher's choice up to 2,048 pairs)",
+        "roofline": {"bound": "fp32", "kernel": "icp_align_pair_kernel<2,pruned,2 warps> (the dispatcher's choice above 512 pairs)",
                      "achieved": evals * 5 / (ms * 1e-3) / 1e12,
                      "peak": fp32_peak, "unit": "TFLOP/s", "frac": evals * 5 / (ms * 1e-3) / 1e12 / fp32_peak,
                      "traffic": None, "note": "tiny ragged problems, less than one wave: bound by the latency of the longest pair"},

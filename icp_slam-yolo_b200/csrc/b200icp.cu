@@ -41,7 +41,7 @@ constexpr int kMaxWarps = 8;       // CTA size limit of the per-pair kernels
 constexpr int kMaxS = 4;           // source points per lane
 constexpr int kMaxSrcPitch = kMaxS * kMaxWarps * 32;   // 1024
 constexpr int kMaxTgtPitch = 4096;
-constexpr int64_t kAutoCtaPairs = 2048;   // at or below: CTA-per-pair fused kernel (latency), above: warp-per-pair (throughput)
+constexpr int64_t kAutoCtaPairs = 512;    // at or below: CTA-per-pair fused kernel (latency), above: W warps per pair (throughput)
 constexpr int kRedStride = 8;      // doubles per warp slot in the staging reductions
 constexpr int kRedStride2 = 12;    // doubles per warp slot in the per-iteration reduction
 constexpr unsigned kFull = 0xffffffffu;
@@ -1982,8 +1982,8 @@ int b200icp_align_batch(const b200icp_problem* prob, int64_t n_pairs, const b200
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // Which fused kernel?  W warps per pair sharing one tile has the best throughput once the pairs
   // fill the GPU (148 SMs x 12 CTAs); below that a pair's latency is what counts and the CTA-per-pair
-  // kernel (up to 8 warps on one pair) is 2-4.6x faster: 0.14 vs 0.52 ms for one 160 x 1,000
-  // scan-to-local-map registration, crossover near 1,000 pairs of 360 x 360 (tools/latency_single.py).
+  // kernel (up to 8 warps on one pair) is ~2x faster: 0.14 vs 0.23 ms for one 160 x 1,000
+  // scan-to-local-map registration, crossover near 500 pairs of 360 x 360 (tools/latency_single.py).
   if (!use_cta_kernel(n_pairs, opt->flags, out->evaluated_pairs != nullptr))
     return launch_pair_kernel(prob, ls, args, (opt->flags & B200ICP_FLAG_DENSE_SWEEP) != 0,
                               (opt->flags >> B200ICP_FLAG_PAIR_WARPS_SHIFT) & 7, st);

@@ -273,7 +273,7 @@ def align_pairs(src: ScanTable, tgt: ScanTable, *, n_pairs: Optional[int] = None
     provably out of reach (identical results; only worth it for spatially unordered point sets).
     ``sweep_reuse=False`` sweeps every pass in every iteration instead of skipping the sweep of a
     pass whose points provably keep their nearest neighbour's group (identical results; A/B knob).
-    ``kernel``: "auto" (CTA-per-pair fused kernel up to 2,048 pairs -- lowest latency --, the
+    ``kernel``: "auto" (CTA-per-pair fused kernel up to 512 pairs -- lowest latency --, the
     W-warps-per-pair throughput kernel above), "warp" (throughput kernel) or "cta".
     ``pair_warps`` forces W (1..4; 0 = auto).
     """
@@ -409,7 +409,7 @@ class HostPipeline:
         self.compute_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         # one fused kernel for every chunk, chosen on the size of the whole batch: results must not
         # depend on how the batch is cut (the two kernels agree to ~1e-12, not bit for bit)
-        self.kernel = "warp" if self.n_pairs > 2048 else "cta"
+        self.kernel = "warp" if self.n_pairs > 512 else "cta"
         pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
         self.h_pose = pin(self.n_pairs, 6, dt=torch.float64)
         self.h_error = pin(self.n_pairs, dt=torch.float64)

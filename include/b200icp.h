@@ -101,12 +101,12 @@ typedef struct b200icp_problem {
 #define B200ICP_FLAG_WARP_KERNEL 4  /* force the throughput kernel (W warps per pair, shared tile)  */
 #define B200ICP_FLAG_CTA_KERNEL 8   /* force the latency kernel (one CTA of up to 8 warps per pair).
                                        Default: chosen by the batch size -- the throughput kernel once
-                                       the pairs fill the GPU (> 2,048), the latency kernel below that
+                                       the pairs fill the GPU (> 512), the latency kernel below that
                                        (one registration per frame).
                                        BATCH-SIZE DEPENDENCE: the two kernels find identical
                                        correspondences and iteration counts but add the float64 sums in
                                        a different order, so the pose bits of one pair may differ by
-                                       ~1e-12 (relative) between a call of <= 2,048 pairs and a larger
+                                       ~1e-12 (relative) between a call of <= 512 pairs and a larger
                                        one.  Callers that need bit-stable poses across batch sizes
                                        force one kernel with these flags (HostPipeline does, on the
                                        size of the whole batch).                                   */

@@ -161,8 +161,8 @@ def test_scan_data_1_all_pairs_full_history(b200, cart_scans, oracle_pairs, gold
     """Config 2: all 1,830 consecutive pairs in one launch; every iteration's correspondence
     vector, the iteration count, the pose and the error against the oracle; the pose also
     against what the unmodified reference produced (golden fixture).  Both fused kernels: the
-    dispatcher picks the CTA-per-pair one for a batch of this size, the warp-per-pair one above
-    2,048 pairs."""
+    dispatcher picks the throughput kernel for a batch of this size, the CTA-per-pair one up to
+    512 pairs."""
     table = b200.ScanTable.from_list(cart_scans)
     res = b200.align_consecutive(table, max_iterations=30, tolerance=1e-5, kernel=kernel,
                                  want_indices=True, want_src=True, want_history=True)
