@@ -42,9 +42,8 @@ def _as_points(a, name: str) -> np.ndarray:
     return np.ascontiguousarray(a[:, :2])
 
 
-def _pose6(init_pose) -> Optional[torch.Tensor]:
-    if init_pose is None:
-        return None
+def _pose6_host(init_pose) -> torch.Tensor:
+    """(R, t) / 3x3 / 4x4 -> host tensor [6] = R00 R01 R10 R11 tx ty."""
     if isinstance(init_pose, (tuple, list)) and len(init_pose) == 2:
         R0, t0 = np.asarray(init_pose[0], dtype=np.float64), np.asarray(init_pose[1], dtype=np.float64)
     else:
@@ -55,8 +54,56 @@ def _pose6(init_pose) -> Optional[torch.Tensor]:
             R0, t0 = T[:2, :2], T[:2, 2]
         else:
             raise ValueError("init_pose must be (R, t), a 3x3 or a 4x4 homogeneous matrix")
-    p = np.concatenate([R0.reshape(4), t0.reshape(2)])[None, :]
-    return torch.from_numpy(np.ascontiguousarray(p)).cuda()
+    return torch.from_numpy(np.ascontiguousarray(np.concatenate([R0.reshape(4), t0.reshape(2)])))
+
+
+def _pose6(init_pose) -> Optional[torch.Tensor]:
+    if init_pose is None:
+        return None
+    return _pose6_host(init_pose)[None, :].cuda()
+
+
+class _CallBuffers:
+    """Pinned host + device staging for ONE alignment of an (n, m) problem: both point sets travel
+    in one host-to-device copy and every output comes back in one device-to-host copy, so a call costs
+    two copies, one launch and one synchronisation (the reference's call is synchronous too)."""
+
+    def __init__(self, n: int, m: int, device):
+        self.n, self.m = n, m
+        n_idx = ((n + 1) // 2 + 1) // 2 * 2        # float64 slots that hold n int32 indices; even, so that
+                                                   # the points behind them stay 16-byte aligned (double2 stores)
+        self.h_in = torch.empty(2 * (n + m), dtype=torch.float64).pin_memory()
+        self.d_in = torch.empty(2 * (n + m), dtype=torch.float64, device=device)
+        self.h_pose = torch.zeros(6, dtype=torch.float64).pin_memory()
+        self.d_pose = torch.empty((1, 6), dtype=torch.float64, device=device)
+        size = 16 + n_idx + 2 * n
+        self.h_out = torch.empty(size, dtype=torch.float64).pin_memory()
+        self.d_out = torch.empty(size, dtype=torch.float64, device=device)
+        d = self.d_out
+        ints = d[14:15].view(torch.int32)
+        from .registration import AlignResult
+        self.out = AlignResult(
+            pose_total=d[0:6].view(1, 6), pose_last=d[6:12].view(1, 6), error=d[12:13], rmse=d[13:14],
+            inliers=ints[0:1], iterations=ints[1:2],
+            indices=d[16:16 + n_idx].view(torch.int32)[:n].view(1, n),
+            src_final=d[16 + n_idx:].view(1, n, 2))
+        self.src = ScanTable(self.d_in[:2 * n].view(1, n, 2), None)
+        self.tgt = ScanTable(self.d_in[2 * n:].view(1, m, 2), None)
+        self.n_idx = n_idx
+
+
+_buffers: "dict[tuple, _CallBuffers]" = {}
+
+
+def _call_buffers(n: int, m: int) -> _CallBuffers:
+    dev = torch.device("cuda", torch.cuda.current_device())
+    key = (n, m, dev.index)
+    buf = _buffers.get(key)
+    if buf is None:
+        if len(_buffers) >= 16:                    # a handful of shapes (the SLAM loop sees few)
+            _buffers.pop(next(iter(_buffers)))
+        buf = _buffers[key] = _CallBuffers(n, m, dev)
+    return buf
 
 
 def icp_full(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_pose=None,
@@ -67,21 +114,30 @@ def icp_full(A, B, max_iterations: int = 20, tolerance: float = 1e-5, *, init_po
     lib = _cabi.lib()
     if len(A) > lib.b200icp_max_src_pitch() or len(B) > lib.b200icp_max_tgt_pitch():
         return _icp_full_large(A, B, max_iterations, tolerance, init_pose, max_corr_dist)
-    src = ScanTable(torch.from_numpy(A[None]).cuda(), None)
-    tgt = ScanTable(torch.from_numpy(B[None]).cuda(), None)
-    res = align_pairs(src, tgt, n_pairs=1, max_iterations=max_iterations, tolerance=tolerance,
-                      init_pose=_pose6(init_pose), max_corr_dist=max_corr_dist,
-                      want_indices=True, want_src=True)
-    pt = res.pose_total[0].cpu().numpy()
-    pl = res.pose_last[0].cpu().numpy()
-    inl = int(res.inliers[0].item())
+    n, m = len(A), len(B)
+    buf = _call_buffers(n, m)
+    hin = buf.h_in.numpy()
+    hin[:2 * n] = A.reshape(-1)
+    hin[2 * n:] = B.reshape(-1)
+    buf.d_in.copy_(buf.h_in, non_blocking=True)
+    pose = None
+    if init_pose is not None:
+        buf.h_pose.copy_(_pose6_host(init_pose))
+        buf.d_pose.copy_(buf.h_pose.view(1, 6), non_blocking=True)
+        pose = buf.d_pose
+    align_pairs(buf.src, buf.tgt, n_pairs=1, max_iterations=max_iterations, tolerance=tolerance,
+                init_pose=pose, max_corr_dist=max_corr_dist, out=buf.out)
+    buf.h_out.copy_(buf.d_out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    o = buf.h_out.numpy()
+    ints = o[14:15].view(np.int32)
     return IcpOutput(
-        R=pt[:4].reshape(2, 2).copy(), t=pt[4:6].copy(),
-        error=float(res.error[0].item()), iterations=int(res.iterations[0].item()),
-        R_last=pl[:4].reshape(2, 2).copy(), t_last=pl[4:6].copy(),
-        rmse=float(res.rmse[0].item()), fitness=inl / float(len(A)),
-        indices=res.indices[0].cpu().numpy().astype(np.intp),
-        src=res.src_final[0].cpu().numpy(),
+        R=o[0:4].reshape(2, 2).copy(), t=o[4:6].copy(),
+        error=float(o[12]), iterations=int(ints[1]),
+        R_last=o[6:10].reshape(2, 2).copy(), t_last=o[10:12].copy(),
+        rmse=float(o[13]), fitness=int(ints[0]) / float(n),
+        indices=o[16:16 + buf.n_idx].view(np.int32)[:n].astype(np.intp),
+        src=o[16 + buf.n_idx:].reshape(n, 2).copy(),
     )
 
 
