@@ -65,6 +65,7 @@ class S2MShard(C.Structure):
         ("points", C.c_void_p), ("m", C.c_int64), ("global_offset", C.c_int64),
         ("dtype", C.c_int32), ("reserved", C.c_int32),
         ("chunk_circle", C.c_void_p), ("super_circle", C.c_void_p),
+        ("sorted_points", C.c_void_p), ("order", C.c_void_p),
     ]
 
 
@@ -113,7 +114,8 @@ SYMBOLS = {
     "b200icp_s2m_padded_chunks": (C.c_int64, [C.c_int64]),
     "b200icp_s2m_scratch_bytes": (C.c_int64, [C.c_int32]),
     "b200icp_s2m_inbox_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
-    "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p]),
+    "b200icp_s2m_prepare_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "b200icp_s2m_prepare_map": (C.c_int, [C.POINTER(S2MShard), C.c_void_p, C.c_int64, C.c_void_p]),
     "b200icp_s2m_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200icp_s2m_search": (C.c_int, [C.POINTER(S2MShard), C.POINTER(S2MTables), C.c_void_p, C.c_void_p,

@@ -34,6 +34,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cub/cub.cuh>
+
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -103,6 +105,95 @@ __device__ __forceinline__ b200icp_s2m_record* inbox_records(void* base, int wor
 }
 __device__ __forceinline__ long long* inbox_flags(void* base, int world, int n) {
   return reinterpret_cast<long long*>(reinterpret_cast<b200icp_s2m_record*>(base) + (int64_t)2 * world * n);
+}
+
+// ------------------------------------------------------------------------------------------
+// prepare (optional): Morton order.  Chunks are runs of 1,024 consecutive points, so the culling
+// needs an order in which neighbours in memory are neighbours in space.  Accumulated LiDAR scans
+// have one; a map that went through a hash-based voxel filter does not.  Sorting the shard once by
+// the Morton code of its points (16 bits per axis inside the shard's bounding box) makes the circles
+// compact for ANY map.  The scan then runs over the sorted copy; `order[j]` is the original index
+// of sorted point j, which is what the records report and what ties are broken on.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f64_ordered(double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unordered(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// box[0..3] = ordered keys of min x, min y, max x, max y (pre-set to ~0, ~0, 0, 0)
+__global__ void __launch_bounds__(256) s2m_bbox_kernel(const void* points, int dtype, int64_t m,
+                                                       unsigned long long* box) {
+  double x0 = CUDART_INF, y0 = CUDART_INF, x1 = -CUDART_INF, y1 = -CUDART_INF;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+    const double2 q = load_point(points, dtype, j);
+    if (q.x == q.x && q.y == q.y) {
+      x0 = fmin(x0, q.x); x1 = fmax(x1, q.x); y0 = fmin(y0, q.y); y1 = fmax(y1, q.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = fmin(x0, __shfl_xor_sync(kFull, x0, o)); x1 = fmax(x1, __shfl_xor_sync(kFull, x1, o));
+    y0 = fmin(y0, __shfl_xor_sync(kFull, y0, o)); y1 = fmax(y1, __shfl_xor_sync(kFull, y1, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(box + 0, f64_ordered(x0)); atomicMin(box + 1, f64_ordered(y0));
+    atomicMax(box + 2, f64_ordered(x1)); atomicMax(box + 3, f64_ordered(y1));
+  }
+}
+
+__device__ __forceinline__ unsigned spread16(unsigned v) {      // abcd -> 0a0b0c0d
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) s2m_morton_kernel(const void* points, int dtype, int64_t m,
+                                                         const unsigned long long* __restrict__ box,
+                                                         unsigned* __restrict__ keys, int32_t* __restrict__ idx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const double x0 = f64_unordered(box[0]), y0 = f64_unordered(box[1]);
+  const double ext = fmax(fmax(f64_unordered(box[2]) - x0, f64_unordered(box[3]) - y0), 1e-300);
+  const double2 q = load_point(points, dtype, j);
+  const double fx = (q.x - x0) / ext * 65535.0, fy = (q.y - y0) / ext * 65535.0;   // one scale: square cells
+  const unsigned qx = (unsigned)fmin(fmax(fx, 0.0), 65535.0), qy = (unsigned)fmin(fmax(fy, 0.0), 65535.0);
+  keys[j] = spread16(qx) | (spread16(qy) << 1);
+  idx[j] = (int32_t)j;
+}
+
+__global__ void __launch_bounds__(256) s2m_gather_kernel(const void* points, int dtype, int64_t m,
+                                                         const int32_t* __restrict__ order, void* sorted) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  if (dtype == B200ICP_F64) reinterpret_cast<double2*>(sorted)[j] = reinterpret_cast<const double2*>(points)[order[j]];
+  else reinterpret_cast<float2*>(sorted)[j] = reinterpret_cast<const float2*>(points)[order[j]];
+}
+
+struct SortWs {
+  int64_t box, keys_in, keys_out, idx_in, cub, total;
+  size_t cub_bytes;
+};
+
+SortWs sort_layout(int64_t m) {
+  auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+  SortWs w;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)m);
+  w.cub_bytes = cub_bytes;
+  int64_t off = 0;
+  w.box = off;      off += 256;
+  w.keys_in = off;  off += up(m * 4);
+  w.keys_out = off; off += up(m * 4);
+  w.idx_in = off;   off += up(m * 4);
+  w.cub = off;      off += up((int64_t)cub_bytes);
+  w.total = off;
+  return w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -217,7 +308,8 @@ __device__ __forceinline__ double2 apply_pending(const b200icp_s2m_state* st, do
 // search: one warp per scan point (see the header of this file)
 // ------------------------------------------------------------------------------------------
 struct SearchArgs {
-  const void* points;          // this rank's shard
+  const void* points;          // this rank's shard as it is scanned (the Morton-sorted copy if there is one)
+  const int32_t* order;        // sorted position -> original local index, or NULL (scanned in the given order)
   int64_t m, global_offset;
   int dtype;
   const double* chunk_circle;  // circles of the whole map (all ranks, rank order)
@@ -244,8 +336,18 @@ __device__ __forceinline__ bool circle_hit(const Circle& c, double sx, double sy
 
 // Exhaustive float64 scan of one chunk for one point: lanes stride over the chunk, eight
 // independent loads in flight per lane, strict < in ascending index per lane.
+// (bd, bp): best squared distance and its position in the scanned array.  Strict < in ascending
+// position keeps the lowest position on exact ties, which is the lowest ORIGINAL index when the map
+// is scanned in its given order; in a Morton-sorted copy exact ties are re-decided on order[].
+__device__ __forceinline__ void consider(const SearchArgs& a, double d, long long pos, double& bd, long long& bp) {
+  if (d <= bd) {
+    if (d < bd) { bd = d; bp = pos; }
+    else if (a.order && bp != kNoIndex && a.order[pos] < a.order[bp]) bp = pos;
+  }
+}
+
 __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double sx, double sy, int lane,
-                                           double& bd, long long& bj) {
+                                           double& bd, long long& bp) {
   const int64_t j0 = (int64_t)lc * kChunk;
   const int cnt = (int)min((int64_t)kChunk, a.m - j0);
   int j = lane;
@@ -256,10 +358,8 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
 #pragma unroll
       for (int u = 0; u < 8; ++u) q[u] = __ldg(p + j + 32 * u);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double d = dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y));
-        if (d < bd) { bd = d; bj = j0 + j + 32 * u; }
-      }
+      for (int u = 0; u < 8; ++u)
+        consider(a, dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y)), j0 + j + 32 * u, bd, bp);
     }
   } else {
     const double2* __restrict__ p = reinterpret_cast<const double2*>(a.points) + j0;
@@ -268,16 +368,10 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
 #pragma unroll
       for (int u = 0; u < 4; ++u) q[u] = __ldg(p + j + 32 * u);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double d = dist2_f64(sx, sy, q[u]);
-        if (d < bd) { bd = d; bj = j0 + j + 32 * u; }
-      }
+      for (int u = 0; u < 4; ++u) consider(a, dist2_f64(sx, sy, q[u]), j0 + j + 32 * u, bd, bp);
     }
   }
-  for (; j < cnt; j += 32) {
-    const double d = dist2_f64(sx, sy, load_point(a.points, a.dtype, j0 + j));
-    if (d < bd) { bd = d; bj = j0 + j; }
-  }
+  for (; j < cnt; j += 32) consider(a, dist2_f64(sx, sy, load_point(a.points, a.dtype, j0 + j)), j0 + j, bd, bp);
 }
 
 constexpr int kSuperBlock = 1024;     // super-chunks per traversal block: one candidate bit per lane and trip
@@ -394,17 +488,18 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
         }
       }
     }
+    long long bo = (bj != kNoIndex && a.order) ? (long long)a.order[bj] : bj;   // original local index
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {                       // lexicographic (distance, index)
+    for (int o = 16; o > 0; o >>= 1) {                       // lexicographic (distance, original index)
       const double od = __shfl_xor_sync(kFull, bd, o);
-      const long long oj = __shfl_xor_sync(kFull, bj, o);
-      if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+      const long long oo = __shfl_xor_sync(kFull, bo, o), oj = __shfl_xor_sync(kFull, bj, o);
+      if (od < bd || (od == bd && oo < bo)) { bd = od; bo = oo; bj = oj; }
     }
     b200icp_s2m_record rec;
     rec.d2 = bd; rec.gidx = kNoIndex; rec.bx = 0.0; rec.by = 0.0;        // "none": the NN is in another shard
     if (bj != kNoIndex) {
       const double2 b = load_point(a.points, a.dtype, bj);
-      rec.gidx = a.global_offset + bj; rec.bx = b.x; rec.by = b.y;
+      rec.gidx = a.global_offset + bo; rec.bx = b.x; rec.by = b.y;
     }
     if (a.peers) {                                           // lane r stores into rank r's inbox
       for (int r = lane; r < a.world; r += 32) inbox_records(a.peers[r], a.world, a.n, slot, a.rank)[i] = rec;
@@ -638,17 +733,49 @@ int64_t b200icp_s2m_inbox_bytes(int32_t n_scan, int32_t world) {
   return (int64_t)2 * world * n_scan * (int64_t)sizeof(b200icp_s2m_record) + (int64_t)(2 * world + 1) * 8;
 }
 
-int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream) {
+int64_t b200icp_s2m_prepare_workspace_bytes(int64_t m) {
+  if (m < 1 || m > 0x7fffffffLL) return -1;
+  return sort_layout(m).total;
+}
+
+int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
   if (!shard || !shard->points || !shard->chunk_circle || !shard->super_circle)
     return fail("s2m_prepare_map: NULL pointer", B200ICP_ERR_INVALID_ARGUMENT);
   if (shard->m < 1) return fail("s2m_prepare_map: empty shard", B200ICP_ERR_INVALID_ARGUMENT);
   if (shard->dtype != B200ICP_F32 && shard->dtype != B200ICP_F64)
     return fail("s2m_prepare_map: bad dtype", B200ICP_ERR_INVALID_ARGUMENT);
+  if ((shard->sorted_points == nullptr) != (shard->order == nullptr))
+    return fail("s2m_prepare_map: sorted_points and order go together", B200ICP_ERR_INVALID_ARGUMENT);
   const int64_t n_chunks = (shard->m + kChunk - 1) / kChunk;
   const int64_t padded = b200icp_s2m_padded_chunks(shard->m);
   if (padded > (1LL << 24)) return fail("s2m_prepare_map: shard too large", B200ICP_ERR_UNSUPPORTED_SHAPE);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  s2m_prepare_kernel<<<(unsigned)padded, 256, 0, st>>>(shard->points, shard->dtype, shard->m, (int)n_chunks,
+  const void* scanned = shard->points;
+  if (shard->sorted_points) {                   // Morton order (see above)
+    if (shard->m > 0x7fffffffLL) return fail("s2m_prepare_map: spatial sort needs m < 2^31", B200ICP_ERR_UNSUPPORTED_SHAPE);
+    const SortWs w = sort_layout(shard->m);
+    if (!workspace || workspace_bytes < w.total) return fail("s2m_prepare_map: workspace too small", B200ICP_ERR_INVALID_ARGUMENT);
+    unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+    unsigned long long* box = reinterpret_cast<unsigned long long*>(base + w.box);
+    unsigned* keys_in = reinterpret_cast<unsigned*>(base + w.keys_in);
+    unsigned* keys_out = reinterpret_cast<unsigned*>(base + w.keys_out);
+    int32_t* idx_in = reinterpret_cast<int32_t*>(base + w.idx_in);
+    if (cudaMemsetAsync(box, 0xff, 16, st) != cudaSuccess || cudaMemsetAsync(box + 2, 0, 16, st) != cudaSuccess)
+      return cuda_check("cudaMemsetAsync");
+    const unsigned blocks = (unsigned)((shard->m + 255) / 256);
+    s2m_bbox_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(shard->points, shard->dtype, shard->m, box);
+    s2m_morton_kernel<<<blocks, 256, 0, st>>>(shard->points, shard->dtype, shard->m, box, keys_in, idx_in);
+    size_t cub_bytes = w.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(base + w.cub, cub_bytes, keys_in, keys_out, idx_in, shard->order,
+                                                    (int)shard->m, 0, 32, st);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e), B200ICP_ERR_CUDA);
+    s2m_gather_kernel<<<blocks, 256, 0, st>>>(shard->points, shard->dtype, shard->m, shard->order, shard->sorted_points);
+    int rc = cuda_check("s2m spatial sort");
+    if (rc) return rc;
+    scanned = shard->sorted_points;
+  }
+  s2m_prepare_kernel<<<(unsigned)padded, 256, 0, st>>>(scanned, shard->dtype, shard->m, (int)n_chunks,
                                                        shard->chunk_circle);
   int rc = cuda_check("s2m_prepare_kernel");
   if (rc) return rc;
@@ -680,7 +807,10 @@ int b200icp_s2m_search(const b200icp_s2m_shard* shard, const b200icp_s2m_tables*
       (int64_t)tables->n_local_chunks != b200icp_s2m_padded_chunks(shard->m))
     return fail("s2m_search: inconsistent circle tables", B200ICP_ERR_INVALID_ARGUMENT);
   SearchArgs a;
-  a.points = shard->points; a.m = shard->m; a.global_offset = shard->global_offset; a.dtype = shard->dtype;
+  if ((shard->sorted_points == nullptr) != (shard->order == nullptr))
+    return fail("s2m_search: sorted_points and order go together", B200ICP_ERR_INVALID_ARGUMENT);
+  a.points = shard->sorted_points ? shard->sorted_points : shard->points; a.order = shard->order;
+  a.m = shard->m; a.global_offset = shard->global_offset; a.dtype = shard->dtype;
   a.chunk_circle = tables->chunk_circle; a.super_circle = tables->super_circle;
   a.n_chunks_total = tables->n_chunks_total; a.first_local_chunk = tables->first_local_chunk;
   a.n_local_chunks = tables->n_local_chunks;

@@ -33,9 +33,15 @@ def _lib():
 
 
 class MapShard:
-    """One rank's contiguous slice of the map and its circle tables."""
+    """One rank's contiguous slice of the map and its circle tables.
 
-    def __init__(self, points: torch.Tensor, global_offset: int = 0, stream=None):
+    ``spatial_sort``: the culling works on runs of 1,024 consecutive map points, so it needs an
+    order in which neighbours in memory are neighbours in space.  True builds a Morton-sorted copy
+    of the shard once (indices and tie-breaking still refer to the original order); False scans the
+    map as given (accumulated LiDAR scans are ordered along the walls already); "auto" sorts when
+    the chunks of the given order are spread out (mean chunk radius above 5 % of the shard's extent)."""
+
+    def __init__(self, points: torch.Tensor, global_offset: int = 0, stream=None, spatial_sort="auto"):
         if points.dim() != 2 or points.shape[1] != 2 or points.dtype not in _DTYPES:
             raise ValueError("map points must be [m, 2] float32/float64")
         _require_cuda(points, "map points")
@@ -55,9 +61,31 @@ class MapShard:
         self.desc.dtype = _DTYPES[points.dtype]
         self.desc.chunk_circle = self.chunk_circle.data_ptr()
         self.desc.super_circle = self.super_circle.data_ptr()
-        with torch.cuda.device(dev):
-            rc = _lib().b200icp_s2m_prepare_map(C.byref(self.desc), _stream_ptr(stream))
+        self.sorted_points = self.order = None
+        if spatial_sort is not True:               # circles of the given order (also the test of "auto")
+            self._prepare(stream)
+        if spatial_sort == "auto" and self.m >= 4 * 1024:
+            valid = self.chunk_circle[:, 2] >= 0
+            extent = float((points.max(dim=0).values - points.min(dim=0).values).max())
+            spatial_sort = bool(float(self.chunk_circle[valid, 2].mean()) > 0.05 * extent)
+        if spatial_sort is True and self.m < 2 ** 31:
+            self.sorted_points = torch.empty_like(points)
+            self.order = torch.empty(self.m, dtype=torch.int32, device=dev)
+            self.desc.sorted_points, self.desc.order = self.sorted_points.data_ptr(), self.order.data_ptr()
+            self._prepare(stream)
+
+    def _prepare(self, stream):
+        ws, nbytes = None, 0
+        if self.order is not None:
+            nbytes = int(_lib().b200icp_s2m_prepare_workspace_bytes(self.m))
+            if nbytes < 0:
+                raise _cabi.B200IcpError("b200icp_s2m_prepare_workspace_bytes failed")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.points.device)
+        with torch.cuda.device(self.points.device):
+            rc = _lib().b200icp_s2m_prepare_map(C.byref(self.desc), _ptr(ws), nbytes, _stream_ptr(stream))
         _cabi.check(rc, "b200icp_s2m_prepare_map")
+        if ws is not None:
+            torch.cuda.current_stream().synchronize()          # the workspace is freed on return
 
 
 class CircleTables:

@@ -234,6 +234,11 @@ typedef struct b200icp_s2m_shard {
   /* filled by b200icp_s2m_prepare_map; caller-allocated, c = b200icp_s2m_padded_chunks(m):    */
   double* chunk_circle;    /* [c][4]: centroid x, y, bounding radius (< 0: padding), unused    */
   double* super_circle;    /* [c / 32][4]: the same for every 32 chunks                        */
+  /* optional, both or neither (caller-allocated): a Morton-sorted copy of the shard, so that the
+   * chunk circles are compact whatever the order of `points` (e.g. after a hash-based voxel filter).
+   * Indices in the records and tie-breaking still refer to the ORIGINAL order.  m < 2^31.       */
+  void* sorted_points;     /* [m][2], same dtype                                               */
+  int32_t* order;          /* [m]: original local index of sorted point j                      */
 } b200icp_s2m_shard;
 
 typedef struct b200icp_s2m_tables {   /* circles of the whole map: every rank's, in rank order */
@@ -267,7 +272,9 @@ typedef struct b200icp_s2m_state {    /* device-resident, 136 bytes */
 int b200icp_s2m_chunk(void);                                   /* 1024                          */
 int64_t b200icp_s2m_padded_chunks(int64_t m);                  /* chunks of a shard, rounded up to 32 */
 int64_t b200icp_s2m_scratch_bytes(int32_t n_scan);             /* tickets + partial sums; ZEROED once by the caller */
-int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* stream);
+int64_t b200icp_s2m_prepare_workspace_bytes(int64_t m);        /* for the spatial sort; not needed without it */
+int b200icp_s2m_prepare_map(const b200icp_s2m_shard* shard, void* workspace /*|NULL*/, int64_t workspace_bytes,
+                            void* stream);
 /* src64 [n][2] float64 scan state (written), prev_nn [n][2] float64 (written: "none"; may be NULL
  * for a one-shot search), state (written) */
 int b200icp_s2m_init(const void* scan, int32_t dtype, int32_t n, const double* init_pose /*[6]|NULL*/,

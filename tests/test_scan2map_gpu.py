@@ -114,3 +114,34 @@ def test_scan_to_map_float64_map_and_unaligned_sizes(b200):
             assert np.array_equal(run.indices.cpu().numpy(), o.indices[it]), (n_shards, it)
         r = run.result()
         assert np.allclose(r.R, o.R_tot, atol=1e-9) and np.allclose(r.t, o.t_tot, atol=1e-6)
+
+
+def test_scan_to_map_spatial_sort_makes_unordered_maps_cullable(b200):
+    """A map in arbitrary order (what a hash-based voxel filter leaves behind): "auto" builds a
+    Morton-sorted copy per shard; indices still refer to the ORIGINAL order and exact ties (duplicated
+    points) still resolve to the lowest original global index, at every iteration."""
+    rng = np.random.default_rng(12)
+    ordered = orc.synth_map(60000, dtype=np.float64)
+    assert b200.MapShard(torch.from_numpy(ordered).cuda()).order is None            # already coherent: scanned as given
+    shuffled = ordered[rng.permutation(len(ordered))]
+    map_pts = np.concatenate([shuffled, shuffled[:700]])                            # exact duplicates, far apart in memory
+    scan = orc.synth_scan_for_map(1000, dtype=np.float64)
+    o = orc.icp_extended(scan, map_pts, 5, -1.0, nn="brute", solver="closed")       # lowest index on ties
+    for n_shards, dtype in ((1, np.float64), (3, np.float64), (2, np.float32)):
+        mp = map_pts.astype(dtype)
+        oo = o if dtype == np.float64 else orc.icp_extended(scan.astype(dtype), mp, 5, -1.0, nn="brute", solver="closed")
+        shards = _shards(b200, mp, n_shards)
+        assert all(s.order is not None for s in shards)
+        run = b200.scan_to_map.ScanToMapLocalShards(shards, len(scan))
+        run.init(torch.from_numpy(scan.astype(dtype)).cuda())
+        for it in range(5):
+            run.step(5, -1.0)
+            assert np.array_equal(run.indices.cpu().numpy(), oo.indices[it]), (n_shards, dtype, it)
+        r = run.result()
+        assert np.allclose(r.R, oo.R_tot, atol=1e-9) and np.allclose(r.t, oo.t_tot, atol=1e-6)
+    # forced on an ordered map: same answers as the unsorted scan
+    a = b200.scan_to_map_icp(torch.from_numpy(scan).cuda(), b200.MapShard(torch.from_numpy(ordered).cuda(), spatial_sort=True),
+                             6, -1.0, want_indices=True)
+    b = b200.scan_to_map_icp(torch.from_numpy(scan).cuda(), b200.MapShard(torch.from_numpy(ordered).cuda(), spatial_sort=False),
+                             6, -1.0, want_indices=True)
+    assert torch.equal(a.indices, b.indices) and a.error == b.error and np.array_equal(a.R, b.R)
