@@ -377,6 +377,7 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
 constexpr int kSuperBlock = 1024;     // super-chunks per traversal block: one candidate bit per lane and trip
 
 __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const SearchArgs a) {
+  __shared__ __align__(16) b200icp_s2m_record srec[kSearchWarps];     // the CTA's records, staged for the peer stores
   b200icp_s2m_state* st = a.state;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -501,13 +502,25 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
       const double2 b = load_point(a.points, a.dtype, bj);
       rec.gidx = a.global_offset + bo; rec.bx = b.x; rec.by = b.y;
     }
-    if (a.peers) {                                           // lane r stores into rank r's inbox
-      for (int r = lane; r < a.world; r += 32) inbox_records(a.peers[r], a.world, a.n, slot, a.rank)[i] = rec;
-    } else if (lane == 0) {
-      a.records[i] = rec;
+    if (lane == 0) {
+      if (a.peers) srec[warp] = rec;
+      else a.records[i] = rec;
     }
   }
-  // ---- (4) last CTA: the pending increment is applied everywhere; raise this rank's flag on every rank.
+  // ---- (4) all-gather as peer stores: the CTA's records are contiguous in every inbox, so warp w
+  // sends them to rank w, w + 8, ... as ONE coalesced store of up to 256 bytes (lane l: 8 bytes)
+  // instead of eight 32-byte stores per point -- NVLink moves few large packets much faster than
+  // many small ones (profiles/r2_kernel_tuning.md)
+  if (a.peers) {
+    __syncthreads();
+    const int first = blockIdx.x * kSearchWarps;
+    const int words = min(kSearchWarps, a.n - first) * 4;               // 8-byte words to send
+    for (int r = warp; r < a.world; r += kSearchWarps) {
+      double* dst = reinterpret_cast<double*>(inbox_records(a.peers[r], a.world, a.n, slot, a.rank) + first);
+      if (lane < words) dst[lane] = reinterpret_cast<const double*>(srec)[lane];
+    }
+  }
+  // last CTA: the pending increment is applied everywhere; raise this rank's flag on every rank.
   // One system-scope fence per CTA (after the barrier: cumulative over the stores of all its warps)
   // orders the records before the ticket, the ticket chain before the last CTA's fence and flag.
   __syncthreads();
