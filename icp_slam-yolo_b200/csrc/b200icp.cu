@@ -637,11 +637,40 @@ struct WarpTile {
 
 constexpr int kCtxBytes = 128;        // PairCtx slot in shared memory
 
-// Candidate sweep over the warp tile (expanded form, packed FFMA2); same contract as
-// nn_candidates<S, true>.
+// Sweep state of the throughput kernel: per source the THREE smallest group minima, each with its
+// group number packed into the low mantissa bits (`keep` = ~((1 << bits) - 1), bits = log2 of the
+// group count).  The keys stay floats -- a few low mantissa bits changed -- so fmin / fmax order
+// them and no select is needed for the group numbers: six ALU operations per group and source.
+// Tracking two groups instead of one is what lets a source keep its candidate set for many
+// iterations: the nearest neighbour of a point near the seam of two groups of 8 flips between
+// them after millimetres of motion, but stays inside their UNION until the point has moved half
+// the gap to the third group.  The perturbation of the keys (relative 2^(bits-23), see key_eps)
+// only widens guard bands: the two candidate groups are re-decided exactly afterwards.
+template <int S>
+struct Cand3 {
+  float kb[S], ks[S], kt[S];
+};
+
+template <int S>
+__device__ __forceinline__ void track3(Cand3<S>& c, int k, float m, unsigned g, unsigned keep) {
+  const float key = __uint_as_float((__float_as_uint(m) & keep) | g);
+  const float b = c.kb[k], s = c.ks[k];
+  c.kt[k] = fminf(c.kt[k], fmaxf(s, key));
+  c.ks[k] = fminf(s, fmaxf(b, key));
+  c.kb[k] = fminf(b, key);
+}
+
+// Absolute error of a packed key: |e| <= 2 (cs + tmax)^2 for the expanded form, relative 2^(bits-23).
+__device__ __forceinline__ float key_eps(float cs, float tmax, unsigned keep) {
+  const float rel = (float)(~keep + 1u) * 1.1920929e-7f;          // 2^bits * 2^-23
+  const float s = cs + tmax;
+  return rel * 2.02f * s * s;
+}
+
+// Candidate sweep over the warp tile (expanded form, packed FFMA2), every group.
 template <int S>
 __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (&sx)[S],
-                                                const float (&sy)[S], Candidates<S>& c) {
+                                                const float (&sy)[S], Cand3<S>& c, unsigned keep) {
   const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile);
   float a[S], b[S];
 #pragma unroll
@@ -649,7 +678,7 @@ __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (
     float vx = -2.0f * sx[k], vy = -2.0f * sy[k];
     asm volatile("" : "+f"(vx), "+f"(vy));
     a[k] = vx; b[k] = vy;
-    c.best[k] = CUDART_INF_F; c.second[k] = CUDART_INF_F; c.group[k] = 0;
+    c.kb[k] = CUDART_INF_F; c.ks[k] = CUDART_INF_F; c.kt[k] = CUDART_INF_F;
   }
   const int ngroups = t.ngroups;
 #pragma unroll 1
@@ -666,7 +695,7 @@ __device__ __forceinline__ void warp_candidates(const WarpTile& t, const float (
       const float2 e67 = __ffma2_rn(ak, make_float2(xb.z, xb.w), __ffma2_rn(bk, make_float2(yb.z, yb.w), make_float2(qb.z, qb.w)));
       const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
                             fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
-      track<S>(c, k, m, g);
+      track3<S>(c, k, m, (unsigned)g, keep);
     }
   }
 }
@@ -689,7 +718,7 @@ __device__ __forceinline__ GroupRegs load_group(const WarpTile& t, int g) {
 
 template <int S>
 __device__ __forceinline__ void eval_group(const GroupRegs& r, int g, const float (&a)[S],
-                                           const float (&b)[S], Candidates<S>& c) {
+                                           const float (&b)[S], Cand3<S>& c, unsigned keep) {
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     const float2 ak = make_float2(a[k], a[k]), bk = make_float2(b[k], b[k]);
@@ -699,7 +728,7 @@ __device__ __forceinline__ void eval_group(const GroupRegs& r, int g, const floa
     const float2 e67 = __ffma2_rn(ak, make_float2(r.xb.z, r.xb.w), __ffma2_rn(bk, make_float2(r.yb.z, r.yb.w), make_float2(r.qb.z, r.qb.w)));
     const float m = fminf(fminf(fminf(e01.x, e01.y), fminf(e23.x, e23.y)),
                           fminf(fminf(e45.x, e45.y), fminf(e67.x, e67.y)));
-    track<S>(c, k, m, g);
+    track3<S>(c, k, m, (unsigned)g, keep);
   }
 }
 
@@ -707,12 +736,12 @@ __device__ __forceinline__ void eval_group(const GroupRegs& r, int g, const floa
 template <int S>
 __device__ __forceinline__ void eval_mask(const WarpTile& t, unsigned mask, int base_g,
                                           const float (&a)[S], const float (&b)[S],
-                                          Candidates<S>& c) {
+                                          Cand3<S>& c, unsigned keep) {
   while (mask) {
     const int g = base_g + __ffs(mask) - 1;
     mask &= mask - 1;
     const GroupRegs r = load_group(t, g);
-    eval_group<S>(r, g, a, b, c);
+    eval_group<S>(r, g, a, b, c, keep);
   }
 }
 
@@ -751,7 +780,8 @@ __device__ __forceinline__ float box_dist2(float px, float py, float x0, float x
 template <int S>
 __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const float (&sx)[S],
                                                       const float (&sy)[S], const bool (&valid)[S],
-                                                      Candidates<S>& c, float reach_scale, float& reach_out) {
+                                                      Cand3<S>& c, unsigned keep, float reach_scale,
+                                                      float& reach_out) {
   int evaluated = 0;            // groups swept in this pass (diagnostics)
   float a[S], b[S], ss[S];
   float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
@@ -759,7 +789,7 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
   for (int k = 0; k < S; ++k) {
     a[k] = -2.0f * sx[k]; b[k] = -2.0f * sy[k];
     ss[k] = fmaf(sx[k], sx[k], sy[k] * sy[k]);
-    c.best[k] = CUDART_INF_F; c.second[k] = CUDART_INF_F; c.group[k] = 0;
+    c.kb[k] = CUDART_INF_F; c.ks[k] = CUDART_INF_F; c.kt[k] = CUDART_INF_F;
     if (valid[k]) {
       x0 = fminf(x0, sx[k]); x1 = fmaxf(x1, sx[k]);
       y0 = fminf(y0, sy[k]); y1 = fmaxf(y1, sy[k]);
@@ -789,14 +819,15 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
     if (w == 1) { d2w1 = d2; rw1 = rr; }
     const unsigned mask = __ballot_sync(kFull, d2 <= rr * rr);
     evaluated += __popc(mask);
-    eval_mask<S>(t, mask, w << 5, a, b, c);
+    eval_mask<S>(t, mask, w << 5, a, b, c, keep);
   }
-  // ---- upper bound of any source's NN distance^2, widened by the ambiguity margin
+  // ---- upper bound of any source's NN distance^2 (the packed key may sit below the value by
+  // key_eps), widened by the ambiguity margin
   float ub2 = 0.f;
 #pragma unroll
   for (int k = 0; k < S; ++k)
-    if (valid[k]) ub2 = fmaxf(ub2, c.best[k] + ss[k]);
-  ub2 = warp_max_f32(ub2);
+    if (valid[k]) ub2 = fmaxf(ub2, c.kb[k] + ss[k]);
+  ub2 = warp_max_f32(ub2) + key_eps(csk, t.tmax, keep);
   // slot-level margin >= every lane's is_ambiguous margin (monotone in cs); + the FP32 rounding
   // of |s|^2 itself (<= 4u * csk^2).  +inf if stage A hit nothing.
   const float margin = expanded_margin(csk, t.tmax);
@@ -820,7 +851,7 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
     const float far = rr + reach;                          // +inf when stage A hit nothing
     const unsigned mask = __ballot_sync(kFull, (w << 5) + lane < ngroups && d2 > rr * rr && d2 <= far * far);
     evaluated += __popc(mask);
-    eval_mask<S>(t, mask, w << 5, a, b, c);
+    eval_mask<S>(t, mask, w << 5, a, b, c, keep);
   }
   return evaluated;
 }
@@ -863,12 +894,14 @@ constexpr int kPairRedStride = 12;   // doubles per warp slot of the cross-warp 
 __host__ __device__ inline size_t pair_tile_bytes(int mcap, int ncap, int passes, int warps) {
   size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
              (size_t)2 * warps * kPairRedStride * sizeof(double) + (size_t)passes * 2 * sizeof(float) +
-             (size_t)(mcap / kGroup) * 3 * sizeof(float) + (size_t)ncap * sizeof(unsigned short);
+             (size_t)(mcap / kGroup) * 3 * sizeof(float) + (size_t)ncap * 2 * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
 
 struct PairTile : WarpTile {
   unsigned short* nnidx;    // [ncap] nearest target of every source at its last search
+  unsigned short* grp2;     // [ncap] the OTHER group of the source's candidate pair (= its own group if alone)
+  unsigned keep;            // mantissa bits a packed sweep key keeps: ~((1 << log2ceil(groups)) - 1)
   float* tgrp;              // [passes] cum_move up to which the sources of a pass keep their GROUP
   float* tnn;               // [passes] ... keep their nearest neighbour
   double* red;              // [2][W][kPairRedStride]
@@ -887,6 +920,10 @@ __device__ __forceinline__ void carve_pair_tile(unsigned char* smem, const Kerne
   t.gcy = t.gcx + a.mcap / kGroup;
   t.grad = t.gcy + a.mcap / kGroup;
   t.nnidx = reinterpret_cast<unsigned short*>(t.grad + a.mcap / kGroup);
+  t.grp2 = t.nnidx + a.ncap;
+  unsigned bits = 1;
+  while ((1u << bits) < (unsigned)(a.mcap / kGroup)) ++bits;
+  t.keep = ~((1u << bits) - 1u);
   t.grp = nullptr; t.tpass = nullptr; t.grp16 = false;
 }
 
@@ -960,92 +997,116 @@ __device__ __forceinline__ void pair_stage_targets(PairTile& t, int tid, int lan
   }
 }
 
-// in_group_argmin plus the two distance bounds the nearest-neighbour reuse needs: `ubd` >= the
-// exact distance from the source to the winning slot, `los` <= the exact distance to every other
-// target of the group (same FP32 error band as the near-tie guard).
-__device__ __forceinline__ int in_group_decide(const WarpTile& t, int g, float fx, float fy,
+// The exact decision inside the (up to) two candidate groups of a source: FP32 direct-difference
+// distances of their 16 targets, the 4-bit slot packed into the low mantissa bits (relative
+// perturbation <= 2^-19, inside the guard), so the argmin and the runner-up are plain min/max
+// chains.  Returns the winning slot (0..7: group ga, 8..15: group gb), whether a runner-up lies
+// inside the FP32 guard band (-> float64 rescan), `ubd` >= the exact distance from the source to
+// the winner and `los` <= the exact distance to every other target of the two groups.
+__device__ __forceinline__ int in_group_decide(const WarpTile& t, int ga, int gb, bool two, float fx, float fy,
                                                bool& near_tie, float& ubd, float& los) {
-  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * g;
-  const float4 xa = g4[0], xb = g4[1];
-  const float4 ya = g4[2], yb = g4[3];
   const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy);
-  const float2 u0 = __fadd2_rn(make_float2(xa.x, xa.y), nx), v0 = __fadd2_rn(make_float2(ya.x, ya.y), ny);
-  const float2 u1 = __fadd2_rn(make_float2(xa.z, xa.w), nx), v1 = __fadd2_rn(make_float2(ya.z, ya.w), ny);
-  const float2 u2 = __fadd2_rn(make_float2(xb.x, xb.y), nx), v2 = __fadd2_rn(make_float2(yb.x, yb.y), ny);
-  const float2 u3 = __fadd2_rn(make_float2(xb.z, xb.w), nx), v3 = __fadd2_rn(make_float2(yb.z, yb.w), ny);
-  const float2 d01 = __ffma2_rn(v0, v0, __fmul2_rn(u0, u0)), d23 = __ffma2_rn(v1, v1, __fmul2_rn(u1, u1));
-  const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
-  const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
   unsigned best = 0x7f800000u, second = 0x7f800000u;
 #pragma unroll
-  for (int u = 0; u < kGroup; ++u) {
-    const unsigned key = (__float_as_uint(ds[u]) & ~7u) | (unsigned)u;
-    second = min(second, max(best, key));
-    best = min(best, key);
+  for (int h = 0; h < 2; ++h) {
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * (h ? gb : ga);
+    const float4 xa = g4[0], xb = g4[1];
+    const float4 ya = g4[2], yb = g4[3];
+    const float2 u0 = __fadd2_rn(make_float2(xa.x, xa.y), nx), v0 = __fadd2_rn(make_float2(ya.x, ya.y), ny);
+    const float2 u1 = __fadd2_rn(make_float2(xa.z, xa.w), nx), v1 = __fadd2_rn(make_float2(ya.z, ya.w), ny);
+    const float2 u2 = __fadd2_rn(make_float2(xb.x, xb.y), nx), v2 = __fadd2_rn(make_float2(yb.x, yb.y), ny);
+    const float2 u3 = __fadd2_rn(make_float2(xb.z, xb.w), nx), v3 = __fadd2_rn(make_float2(yb.z, yb.w), ny);
+    const float2 d01 = __ffma2_rn(v0, v0, __fmul2_rn(u0, u0)), d23 = __ffma2_rn(v1, v1, __fmul2_rn(u1, u1));
+    const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
+    const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      unsigned key = (__float_as_uint(ds[u]) & ~15u) | (unsigned)(8 * h + u);       // d >= 0: bits are ordered
+      if (h == 1 && !two) key = 0x7f000000u | (unsigned)(8 + u);                     // no second group: never wins
+      second = min(second, max(best, key));
+      best = min(best, key);
+    }
   }
-  const float bd = __uint_as_float(best & ~7u), sd = __uint_as_float(second & ~7u);
+  const float bd = __uint_as_float(best & ~15u), sd = __uint_as_float(second & ~15u);
   const float cs = fmaxf(fabsf(fx), fabsf(fy));
   const float guard = (cs + t.tmax) * 4.76837158e-7f;                // 2^-21 (cs + tmax)
   ubd = sqrtf(bd) * 1.000004f + guard;
   near_tie = sd <= ubd * ubd * 1.000001f;
   los = sqrtf(sd) * 0.999996f - guard;
-  return (int)(best & 7u);
+  return (int)(best & 15u);
 }
 
 // Phase 1 for one pass: the exact nearest target of the SC sources (base + k*32 + lane) of every
-// lane -> t.nnidx.  `reuse_grp`: no sweep, re-decide inside the group of the stored index.
-// bud_grp / bud_nn (identical in every lane on return): how far the sources of this pass may move
-// before one of them can leave its group / change its nearest neighbour; <= 0 means "no bound".
+// lane -> t.nnidx, and the other group of its candidate pair -> t.grp2.  `reuse_grp`: no sweep,
+// re-decide inside the two stored groups.  bud_grp / bud_nn (identical in every lane on return):
+// how far the sources of this pass may move before the nearest neighbour of one of them can leave
+// its two groups / change at all; <= 0 means "no bound".
 template <int SC, bool PRUNE>
 __device__ __forceinline__ long long pair_search_pass(const PairTile& t, int base, int n, int m, int lane,
                                                       bool reuse_grp, bool track, float& bud_grp,
                                                       float& bud_nn) {
   long long evals = 0;
   float fx[SC], fy[SC], lbg[SC];
+  int ga[SC], gb[SC];
+  bool two[SC], amb3[SC];
 #pragma unroll
   for (int k = 0; k < SC; ++k) {
     const double2 s = t.src[base + k * 32 + lane];
     fx[k] = (float)(s.x - t.ox); fy[k] = (float)(s.y - t.oy);
     lbg[k] = -1.f;
+    amb3[k] = false;
   }
-  Candidates<SC> c;
   if (reuse_grp) {
 #pragma unroll
     for (int k = 0; k < SC; ++k) {
       const int i = base + k * 32 + lane;
-      c.group[k] = i < n ? (int)(t.nnidx[i] >> 3) : 0;
-      c.best[k] = 0.f; c.second[k] = CUDART_INF_F;        // cross-group guard: settled by the movement bound
-    }
-  } else if (PRUNE) {
-    bool vld[SC];
-#pragma unroll
-    for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
-    float reach;
-    const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c, track ? 2.0f : 1.0f, reach);
-    evals += (long long)groups * kGroup * min(32 * SC, n - base);
-    if (track) {
-#pragma unroll
-      for (int k = 0; k < SC; ++k) lbg[k] = reach * 0.999996f;
+      ga[k] = i < n ? (int)(t.nnidx[i] >> 3) : 0;
+      gb[k] = i < n ? (int)t.grp2[i] : 0;
+      two[k] = gb[k] != ga[k];                           // a lone group is stored twice
     }
   } else {
-    warp_candidates<SC>(t, fx, fy, c);
-    evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
-    if (track) {
+    Cand3<SC> c;
+    const unsigned keep = t.keep;
+    if (PRUNE) {
+      bool vld[SC];
 #pragma unroll
-      for (int k = 0; k < SC; ++k) lbg[k] = CUDART_INF_F;
+      for (int k = 0; k < SC; ++k) vld[k] = base + k * 32 + lane < n;
+      float reach;
+      const int groups = warp_candidates_pruned<SC>(t, fx, fy, vld, c, keep, track ? 2.0f : 1.0f, reach);
+      evals += (long long)groups * kGroup * min(32 * SC, n - base);
+      if (track) {
+#pragma unroll
+        for (int k = 0; k < SC; ++k) lbg[k] = reach * 0.999996f;
+      }
+    } else {
+      warp_candidates<SC>(t, fx, fy, c, keep);
+      evals += (long long)t.ngroups * kGroup * min(32 * SC, n - base);
+      if (track) {
+#pragma unroll
+        for (int k = 0; k < SC; ++k) lbg[k] = CUDART_INF_F;
+      }
     }
-  }
-  if (track && !reuse_grp) {
 #pragma unroll
     for (int k = 0; k < SC; ++k) {
-      // runner-up group: d^2 >= second + |s|^2 - (FP32 error of the expanded form and of |s|^2)
       const float cs = fmaxf(fabsf(fx[k]), fabsf(fy[k]));
-      const float ss = fmaf(fx[k], fx[k], fy[k] * fy[k]);
-      const float lo2 = (c.second[k] + ss) - (2.f * expanded_margin(cs, t.tmax) + cs * cs * 4.8e-7f);
-      lbg[k] = fminf(lbg[k], sqrtf(fmaxf(lo2, 0.f)) * 0.999996f);
+      const float ek = key_eps(cs, t.tmax, keep);
+      const float margin = expanded_margin(cs, t.tmax);
+      ga[k] = (int)(__float_as_uint(c.kb[k]) & ~keep);
+      two[k] = c.ks[k] < CUDART_INF_F;
+      gb[k] = two[k] ? (int)(__float_as_uint(c.ks[k]) & ~keep) : ga[k];
+      // a THIRD group inside the error band of the best: the nearest neighbour may lie outside the
+      // two candidates -> float64 rescan of all targets (near-equal floats subtract exactly)
+      amb3[k] = (c.kt[k] - c.kb[k]) <= margin + 2.f * ek;
+      if (track) {
+        // every group but the two candidates: d^2 >= third + |s|^2 - (FP32 error of the expanded
+        // form, of |s|^2 and of the packed key)
+        const float ss = fmaf(fx[k], fx[k], fy[k] * fy[k]);
+        const float lo2 = (c.kt[k] + ss) - (2.f * margin + cs * cs * 4.8e-7f + ek);
+        lbg[k] = fminf(lbg[k], sqrtf(fmaxf(lo2, 0.f)) * 0.999996f);
+      }
     }
   }
-  int j[SC];
+  int j[SC], other[SC];
   bool amb[SC];
   bool any_amb = false;
   float bg = CUDART_INF_F, bn = CUDART_INF_F;
@@ -1053,10 +1114,11 @@ __device__ __forceinline__ long long pair_search_pass(const PairTile& t, int bas
   for (int k = 0; k < SC; ++k) {
     bool tie_in;
     float ubd, los;
-    const int slot = in_group_decide(t, c.group[k], fx[k], fy[k], tie_in, ubd, los);
-    j[k] = c.group[k] * kGroup + slot;
+    const int slot = in_group_decide(t, ga[k], gb[k], two[k], fx[k], fy[k], tie_in, ubd, los);
+    j[k] = (slot < 8 ? ga[k] : gb[k]) * kGroup + (slot & 7);
+    other[k] = slot < 8 ? gb[k] : ga[k];
     const bool valid = base + k * 32 + lane < n;
-    amb[k] = valid && (tie_in || (!reuse_grp && is_ambiguous(c.best[k], c.second[k], fx[k], fy[k], t.tmax)));
+    amb[k] = valid && (tie_in || amb3[k]);
     any_amb |= amb[k];
     if (valid) {
       // an ambiguous source is re-decided in float64 below: no FP32 bound describes that decision
@@ -1089,13 +1151,17 @@ __device__ __forceinline__ long long pair_search_pass(const PairTile& t, int bas
         }
         if (lane == owner) jk = lj;
       }
+      if (amb[k]) {                                      // keep (winner's group, one of the old candidates)
+        const int gj = jk >> 3;
+        other[k] = gj == ga[k] ? gb[k] : ga[k];
+      }
       j[k] = jk;
     }
   }
 #pragma unroll
   for (int k = 0; k < SC; ++k) {
     const int i = base + k * 32 + lane;
-    if (i < n) t.nnidx[i] = (unsigned short)j[k];
+    if (i < n) { t.nnidx[i] = (unsigned short)j[k]; t.grp2[i] = (unsigned short)other[k]; }
   }
   bud_nn = warp_min_f32(bn);
   bud_grp = (track && !reuse_grp) ? warp_min_f32(bg) : -1.f;
@@ -1108,7 +1174,8 @@ __device__ __forceinline__ long long pair_search_pass(const PairTile& t, int bas
 // LEAN: float32 tables, no gate, no per-point index outputs (the throughput configuration): the
 // float64 phase is compiled without the corresponding tests and without the inlier count.
 template <int SC, bool PRUNE, int W, bool LEAN>
-__global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_align_pair_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(32 * W, (PRUNE ? B200ICP_PAIR_RESIDENT_WARPS : 16) / W)
+icp_align_pair_kernel(const KernelArgs a) {      // (the dense sweep holds 6 sources per lane: 128 registers, 16 warps)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = 32 * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1182,7 +1249,9 @@ __global__ void __launch_bounds__(32 * W, B200ICP_PAIR_RESIDENT_WARPS / W) icp_a
 
     for (int it = 0; it < op.max_iterations; ++it) {       // icp.py:35
       // ---- phase 1: correspondence search (icp.py:37-38), only where the movement bound demands it
-      const bool track = a.reuse != 0 && (double)mv_prev < 0.5 * prev_error;
+      // every sweep also yields the bounds of the reuse (the two-group budget usually survives even
+      // the large moves of the first iterations)
+      const bool track = a.reuse != 0;
       for (int pass = warp; pass < a.passes; pass += W) {
         const int base = pass * 32 * SC;
         if (base >= n) break;
