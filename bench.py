@@ -432,7 +432,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {
             "bound": "fp32",
-            "kernel": "icp_align_pair_kernel<4,dense,3 warps> (B200ICP_FLAG_DENSE_SWEEP | B200ICP_FLAG_NO_SWEEP_REUSE): "
+            "kernel": "icp_align_pair_kernel<6,dense,2 warps> (B200ICP_FLAG_DENSE_SWEEP | B200ICP_FLAG_NO_SWEEP_REUSE): "
                       "every one of the N_src x N_tgt x 30 pair evaluations SURVEY.md 8(d) counts is executed, so "
                       "achieved/peak is a hardware utilisation",
             "achieved": dense_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": dense_tflops / fp32_peak,
@@ -442,8 +442,9 @@ def run_b200(args):
             "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of the SHIPPED kernel, "
                                "profiles/r2_pair_kernel_ncu.json (ncu --set full, same command)") if ncu else None,
             "shipped_kernel": {
-                "kernel": "icp_align_pair_kernel<2,pruned,2 warps> (exact culling of target groups + nearest-neighbour "
-                          "reuse; bit-identical results, asserted against the dense launch in this run)",
+                "kernel": "icp_align_pair_kernel<2,pruned,2 warps> (exact culling of target groups, two candidate groups "
+                          "per source, movement-bound reuse; bit-identical results, asserted against the dense "
+                          "launch in this run)",
                 "kernel_ms": kernel_ms,
                 "algorithmic_tflops": alg_tflops,
                 "algorithmic_speedup_vs_dense": dense_ms / kernel_ms,
