@@ -176,7 +176,7 @@ def run_reference(args):
                                                     "sample": f"{n1} pairs, one process"}},
         "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -465,7 +465,7 @@ def run_b200(args):
         line["cpu_baseline"] = cpu_base
     if secondary is not None:
         line["secondary"] = secondary
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -674,7 +674,7 @@ def run_odometry(args, ctx=None):
     }
     assert gpu_its == its, (gpu_its, its)
     if ctx is None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     return line
 
 
@@ -742,7 +742,7 @@ def run_allpairs(args, ctx=None):
         "cpu_baseline": (ctx.cpu_sec.get("allpairs") if ctx is not None else None),
     }
     if ctx is None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     return line
 
 
@@ -779,7 +779,7 @@ def run_single(args, ctx=None):
     out["note"] = ("replicas only (SURVEY.md 8e): a single small alignment is launch- and copy-latency bound on a GPU "
                    "(one CTA of work); reported for completeness, wall clock around the Python call")
     if ctx is None:
-        print(json.dumps({"metric": "single ICP alignment latency (configs[0])", "unit": "ms", **out}), flush=True)
+        emit({"metric": "single ICP alignment latency (configs[0])", "unit": "ms", **out})
     return out
 
 
@@ -830,7 +830,7 @@ def run_nn(args, ctx=None, tables=None):
                                      "pruned search alone is closer to the HBM roof than to the FP32 one"}},
     }
     if ctx is None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     return line
 
 
@@ -923,7 +923,7 @@ def run_scan2map(args, ctx=None):
         "cpu_baseline": cpu,
     }
     if ctx is None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     return line
 
 
@@ -1058,7 +1058,7 @@ def run_occupancy(args):
                          "sample": f"first {SAMPLE} frames of the same replay, pure-Python port of process.py:86-177 "
                                    f"({py_wall:.2f} s); C restatement, all {F} frames: {c_wall:.3f} s = {F / c_wall:.0f} frames/s; {cpu_model()}"},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_slam(args):
@@ -1112,11 +1112,31 @@ def run_slam(args):
         "note": "launch- and synchronisation-bound (a dozen small launches and three device-to-host reads per "
                 "frame); reported for completeness, not a roofline workload",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def _keep_stdout_for_the_result():
+    """Libraries print to fd 1 behind Python's back (NCCL's "NCCL version ..." banner when the box sets NCCL_DEBUG):
+    point fd 1 at stderr for everything but the result line."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def main():
     args = parse()
+    _keep_stdout_for_the_result()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "odometry":
