@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline workload only (no `secondary` block)")
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="A/B: allocate the pinned host tables wherever the process happens to run instead of on the "
+                         "GPU's NUMA node (hostmem.near_gpu)")
     ap.add_argument("--workload", default="pairs", choices=["pairs", "odometry", "allpairs", "scan2map", "single", "nn", "occupancy", "slam"],
                     help="pairs = the headline configs[2] (default); the others are BASELINE.json "
                          "configs[1], [3] and [4], reported with the same JSON shape")
@@ -292,8 +295,11 @@ def run_b200(args):
     P = args.pairs
     first = rank * P
     src_np, tgt_np = orc.synth_room_batch(first, P)              # float32, values generated in float64
-    h_src = torch.from_numpy(src_np).pin_memory()
-    h_tgt = torch.from_numpy(tgt_np).pin_memory()
+    if args.no_numa_bind:
+        h_src, h_tgt, numa = torch.from_numpy(src_np).pin_memory(), torch.from_numpy(tgt_np).pin_memory(), None
+    else:                                   # pinned tables on the GPU's NUMA node (matters once 8 GPUs copy at once)
+        h_src, numa = m.hostmem.pin_near_gpu(src_np, local)
+        h_tgt, _ = m.hostmem.pin_near_gpu(tgt_np, local)
     src = m.ScanTable(h_src.to(dev))
     tgt = m.ScanTable(h_tgt.to(dev))
     out = m.alloc_outputs(P, N_POINTS, dev)
@@ -390,6 +396,7 @@ def run_b200(args):
         e2e = {"value": world * P / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "launches_per_step": pipe.launches,
                "h2d_only_ms": h2d_ms, "h2d_only_gbs_per_gpu": h2d / (h2d_ms * 1e-3) / 1e9,
+               "host_numa": numa if numa is not None else "not bound (--no-numa-bind)",
                "limiter": ("host-to-device copy" if h2d_ms > 0.9 * e2e_ms else "kernel") +
                           ": e2e = max(kernel, copy) + the first chunk's copy; h2d_only_ms is the copy alone with every "
                           "rank copying at once (GPUs share host memory and PCIe uplinks)",

@@ -15,7 +15,7 @@ from .scan_to_map import MapShard, ScanToMap, ScanToMapResult, scan_to_map_icp  
 from .mapping import crop_local_map, remove_dynamic_points, voxel_down_sample   # noqa: F401
 from .occupancy import OccupancyGrid                           # noqa: F401
 from .slam import OfflineSlam, SlamConfig                      # noqa: F401
-from . import map_io, scan_io                                  # noqa: F401
+from . import hostmem, map_io, scan_io                         # noqa: F401
 
 __all__ = [
     "B200IcpError", "lib", "library_path", "IcpOutput", "icp", "icp_full", "nearest_neighbors",
@@ -23,5 +23,5 @@ __all__ = [
     "nn_search", "polar_to_cartesian", "align_consecutive", "chain_poses", "shard_range",
     "triangle_pair", "triangle_pair_count", "scan_io", "MapShard", "ScanToMap", "ScanToMapResult",
     "scan_to_map_icp", "crop_local_map", "remove_dynamic_points", "voxel_down_sample",
-    "OccupancyGrid", "map_io", "OfflineSlam", "SlamConfig",
+    "OccupancyGrid", "map_io", "hostmem", "OfflineSlam", "SlamConfig",
 ]

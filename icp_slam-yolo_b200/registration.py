@@ -410,10 +410,12 @@ class HostPipeline:
         # one fused kernel for every chunk, chosen on the size of the whole batch: results must not
         # depend on how the batch is cut (the two kernels agree to ~1e-12, not bit for bit)
         self.kernel = "warp" if self.n_pairs > 512 else "cta"
-        pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-        self.h_pose = pin(self.n_pairs, 6, dt=torch.float64)
-        self.h_error = pin(self.n_pairs, dt=torch.float64)
-        self.h_iters = pin(self.n_pairs, dt=torch.int32)
+        pin = lambda *shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+        from . import hostmem
+        with hostmem.near_gpu(self.device.index if self.device.index is not None else torch.cuda.current_device()):
+            self.h_pose = pin(self.n_pairs, 6, dt=torch.float64)       # result buffers on the GPU's NUMA node
+            self.h_error = pin(self.n_pairs, dt=torch.float64)
+            self.h_iters = pin(self.n_pairs, dt=torch.int32)
         self.launches = 0
         self.done_event = None
 

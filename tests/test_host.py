@@ -173,3 +173,33 @@ def test_map_io_pcd_and_png_round_trip(tmp_path):
     ref_png = "/root/reference/realtime_occupancy_map.png"
     if cv2 is not None and os.path.exists(ref_png):
         assert np.array_equal(pkg.map_io.read_png(ref_png), cv2.imread(ref_png, cv2.IMREAD_UNCHANGED))
+
+
+def test_hostmem_topology_parsing_and_binding(pkg, tmp_path, monkeypatch):
+    """hostmem.near_gpu: reads the GPU's NUMA node from sysfs, binds the thread for the block and restores it;
+    degrades to a recorded no-op when the platform says nothing."""
+    hm = pkg.hostmem
+    assert hm.parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11} and hm.parse_cpulist("") == set()
+    sysfs = tmp_path / "sys"
+    dev = sysfs / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    mine = sorted(os.sched_getaffinity(0))
+    for node, cpus in ((0, mine[:1]), (1, mine[-1:])):
+        d = sysfs / f"devices/system/node/node{node}"
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(",".join(map(str, cpus)) + "\n")
+    (sysfs / "devices/system/node/online").write_text("0-1\n")
+    monkeypatch.setattr(hm, "gpu_pci_address", lambda i: "0000:1b:00.0")
+    monkeypatch.setattr(hm, "_set_mempolicy", lambda mode, node: False)
+    (dev / "numa_node").write_text("-1\n")                       # VM without NUMA information
+    with hm.near_gpu(0, sysfs=str(sysfs)) as rec:
+        assert rec["node"] is None and not rec["bound"] and "no NUMA node" in rec["why"]
+    (dev / "numa_node").write_text("1\n")
+    before = os.sched_getaffinity(0)
+    with hm.near_gpu(0, sysfs=str(sysfs)) as rec:
+        assert rec["node"] == 1 and rec["host_nodes"] == [0, 1] and rec["bound"]
+        assert os.sched_getaffinity(0) == {mine[-1]}
+    assert os.sched_getaffinity(0) == before
+    (sysfs / "devices/system/node/online").write_text("0\n")
+    with hm.near_gpu(0, sysfs=str(sysfs)) as rec:
+        assert not rec["bound"] and rec["why"] == "single NUMA node"
