@@ -880,6 +880,42 @@ __device__ __forceinline__ int warp_candidates_pruned(const WarpTile& t, const f
 // else full (pruned or dense) sweep.  Every level yields the exact float64 nearest neighbour
 // (lowest index on ties), so index histories are identical to the sweep-everything kernel.
 // ------------------------------------------------------------------------------------
+// Warp sums of ten per-lane doubles.  The xor butterfly (16, 8, 4, 2, 1) over all ten values costs
+// 50 shuffle+add pairs; here every step lets a lane KEEP half of its values and SEND the other half
+// to its partner, so the value count halves with the lane distance: 5 + 3 + 2 + 1 + 1 = 12 pairs.
+// Each surviving partial is formed by exactly the additions the butterfly performs for that value
+// (own + partner's, partner distances in the same order), so the sums carry the same bits.
+// On return the lanes with fold10_owner(lane) = q >= 0 hold the warp sum of r[q].
+__device__ __forceinline__ double warp_fold10(const double (&r)[11], int lane) {
+  const bool s16 = lane & 16, s8 = lane & 8, s4 = lane & 4, s2 = lane & 2;
+  double a[5], b[3], c[2];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const double keep = s16 ? r[q + 5] : r[q], send = s16 ? r[q] : r[q + 5];
+    a[q] = keep + __shfl_xor_sync(kFull, send, 16);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double keep = s8 ? a[q + 3] : a[q], send = s8 ? a[q] : a[q + 3];
+    b[q] = keep + __shfl_xor_sync(kFull, send, 8);
+  }
+  b[2] = a[2] + __shfl_xor_sync(kFull, a[2], 8);          // valid in the lanes that kept a[0..2]
+  {
+    const double keep = s4 ? b[2] : b[0], send = s4 ? b[0] : b[2];
+    c[0] = keep + __shfl_xor_sync(kFull, send, 4);
+  }
+  c[1] = b[1] + __shfl_xor_sync(kFull, b[1], 4);          // valid in the lanes that kept b[0..1]
+  const double keep = s2 ? c[1] : c[0], send = s2 ? c[0] : c[1];
+  double d = keep + __shfl_xor_sync(kFull, send, 2);
+  d += __shfl_xor_sync(kFull, d, 1);
+  return d;
+}
+__device__ __forceinline__ int fold10_owner(int lane) {
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+  const bool valid = !(lane & 1) && !(b3 & b2) && !(b2 & b1);
+  return valid ? 5 * b4 + 3 * b3 + 2 * b2 + b1 : -1;
+}
+
 struct PairCtx {            // shared memory; touched by thread 0 only until the final barrier
   double R[4], T[2];        // cumulative pose, src = R A + T
   double last[4];           // last increment: cos, sin, tx, ty
@@ -891,10 +927,17 @@ static_assert(sizeof(PairCtx) <= kCtxBytes, "PairCtx outgrew its shared-memory s
 
 constexpr int kPairRedStride = 12;   // doubles per warp slot of the cross-warp reduction
 
+constexpr int kPairMaxPasses = 16;    // 1,024 sources / 64: the threshold arrays have a fixed size
+
+// Shared-memory layout of a pair: everything of fixed size first (PairCtx, reduction slots, the
+// per-pass thresholds), so that with W a template parameter their addresses are immediates; then the
+// source state, the target tile, the group circles and the per-source indices.
 __host__ __device__ inline size_t pair_tile_bytes(int mcap, int ncap, int passes, int warps) {
-  size_t b = (size_t)mcap * 3 * sizeof(float) + (size_t)ncap * sizeof(double2) + kCtxBytes +
-             (size_t)2 * warps * kPairRedStride * sizeof(double) + (size_t)passes * 2 * sizeof(float) +
-             (size_t)(mcap / kGroup) * 3 * sizeof(float) + (size_t)ncap * 2 * sizeof(unsigned short);
+  (void)passes;
+  size_t b = kCtxBytes + (size_t)2 * warps * kPairRedStride * sizeof(double) +
+             (size_t)2 * kPairMaxPasses * sizeof(float) + (size_t)ncap * sizeof(double2) +
+             (size_t)mcap * 3 * sizeof(float) + (size_t)(mcap / kGroup) * 3 * sizeof(float) +
+             (size_t)ncap * 2 * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
 
@@ -910,13 +953,13 @@ struct PairTile : WarpTile {
 __device__ __forceinline__ void carve_pair_tile(unsigned char* smem, const KernelArgs& a, int warps,
                                                 PairTile& t, PairCtx*& ctx) {
   t.mcap = a.mcap;
-  t.tile = reinterpret_cast<float*>(smem);
-  t.src = reinterpret_cast<double2*>(t.tile + 3 * a.mcap);
-  ctx = reinterpret_cast<PairCtx*>(t.src + a.ncap);
-  t.red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ctx) + kCtxBytes);
+  ctx = reinterpret_cast<PairCtx*>(smem);
+  t.red = reinterpret_cast<double*>(smem + kCtxBytes);
   t.tgrp = reinterpret_cast<float*>(t.red + 2 * warps * kPairRedStride);
-  t.tnn = t.tgrp + a.passes;
-  t.gcx = t.tnn + a.passes;
+  t.tnn = t.tgrp + kPairMaxPasses;
+  t.src = reinterpret_cast<double2*>(t.tnn + kPairMaxPasses);
+  t.tile = reinterpret_cast<float*>(t.src + a.ncap);
+  t.gcx = t.tile + 3 * a.mcap;
   t.gcy = t.gcx + a.mcap / kGroup;
   t.grad = t.gcy + a.mcap / kGroup;
   t.nnidx = reinterpret_cast<unsigned short*>(t.grad + a.mcap / kGroup);
@@ -1003,12 +1046,23 @@ __device__ __forceinline__ void pair_stage_targets(PairTile& t, int tid, int lan
 // chains.  Returns the winning slot (0..7: group ga, 8..15: group gb), whether a runner-up lies
 // inside the FP32 guard band (-> float64 rescan), `ubd` >= the exact distance from the source to
 // the winner and `los` <= the exact distance to every other target of the two groups.
+// (smallest, second smallest) of two such pairs: three operations (min, max, 3-input min).
+__device__ __forceinline__ void merge_two_smallest(unsigned& lo, unsigned& hi, unsigned lo2, unsigned hi2) {
+  const unsigned m = max(lo, lo2);
+  lo = min(lo, lo2);
+  hi = min(min(hi, hi2), m);
+}
+
 __device__ __forceinline__ int in_group_decide(const WarpTile& t, int ga, int gb, bool two, float fx, float fy,
                                                bool& near_tie, float& ubd, float& los) {
-  const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy);
+  const float2 ny = make_float2(-fy, -fy);
   unsigned best = 0x7f800000u, second = 0x7f800000u;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
+    // no second group: its targets are evaluated from 1e18 away (d ~ 1e36, finite also for the
+    // sentinels at +1e18): they never win and never come near the winner
+    const float hx = (h == 1 && !two) ? 1e18f : -fx;
+    const float2 nx = make_float2(hx, hx);
     const float4* __restrict__ g4 = reinterpret_cast<const float4*>(t.tile) + 6 * (h ? gb : ga);
     const float4 xa = g4[0], xb = g4[1];
     const float4 ya = g4[2], yb = g4[3];
@@ -1019,13 +1073,18 @@ __device__ __forceinline__ int in_group_decide(const WarpTile& t, int ga, int gb
     const float2 d01 = __ffma2_rn(v0, v0, __fmul2_rn(u0, u0)), d23 = __ffma2_rn(v1, v1, __fmul2_rn(u1, u1));
     const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
     const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
+    unsigned key[8];
 #pragma unroll
-    for (int u = 0; u < kGroup; ++u) {
-      unsigned key = (__float_as_uint(ds[u]) & ~15u) | (unsigned)(8 * h + u);       // d >= 0: bits are ordered
-      if (h == 1 && !two) key = 0x7f000000u | (unsigned)(8 + u);                     // no second group: never wins
-      second = min(second, max(best, key));
-      best = min(best, key);
-    }
+    for (int u = 0; u < kGroup; ++u)
+      key[u] = (__float_as_uint(ds[u]) & ~15u) | (unsigned)(8 * h + u);             // d >= 0: bits are ordered
+    // tournament instead of a 16-long dependent min/max chain: 17 operations per group, depth 4
+    unsigned lo[4], hi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { lo[u] = min(key[2 * u], key[2 * u + 1]); hi[u] = max(key[2 * u], key[2 * u + 1]); }
+    merge_two_smallest(lo[0], hi[0], lo[1], hi[1]);
+    merge_two_smallest(lo[2], hi[2], lo[3], hi[3]);
+    merge_two_smallest(lo[0], hi[0], lo[2], hi[2]);
+    merge_two_smallest(best, second, lo[0], hi[0]);
   }
   const float bd = __uint_as_float(best & ~15u), sd = __uint_as_float(second & ~15u);
   const float cs = fmaxf(fabsf(fx), fabsf(fy));
@@ -1335,25 +1394,28 @@ icp_align_pair_kernel(const KernelArgs a) {      // (the dense sweep holds 6 sou
         }
       }
       constexpr int NR = LEAN ? 10 : 11;                   // LEAN: no gate, the inlier count is n
+      {         // warp sums, then one hop across the warps; every thread adds the partials in warp order
+        const double mine = warp_fold10(r, lane);
+        if (!LEAN) {
 #pragma unroll
-      for (int q = 0; q < NR; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r[q] += __shfl_xor_sync(kFull, r[q], o);
-      }
-      if (W > 1) {            // one hop across the warps; every thread adds the partials in warp order
-        double* slot = t.red + ((it & 1) * W + warp) * kPairRedStride;
-        if (lane == 0) {
-#pragma unroll
-          for (int q = 0; q < NR; ++q) slot[q] = r[q];
+          for (int o = 16; o > 0; o >>= 1) r[10] += __shfl_xor_sync(kFull, r[10], o);
         }
-        __syncthreads();
-        const double* part = t.red + (it & 1) * W * kPairRedStride;
+        double* slot = t.red + ((it & 1) * W + warp) * kPairRedStride;
+        const int q = fold10_owner(lane);
+        if (q >= 0) slot[q] = mine;
+        if (!LEAN && lane == 0) slot[10] = r[10];
+        if (W > 1) __syncthreads(); else __syncwarp();
+        const double2* part = reinterpret_cast<const double2*>(t.red + (it & 1) * W * kPairRedStride);
 #pragma unroll
-        for (int q = 0; q < NR; ++q) {
-          double acc = part[q];
+        for (int q2 = 0; q2 < (NR + 1) / 2; ++q2) {
+          double2 acc = part[q2];
 #pragma unroll
-          for (int w = 1; w < W; ++w) acc += part[w * kPairRedStride + q];
-          r[q] = acc;
+          for (int w = 1; w < W; ++w) {
+            const double2 o = part[w * (kPairRedStride / 2) + q2];
+            acc.x += o.x; acc.y += o.y;
+          }
+          r[2 * q2] = acc.x;
+          if (2 * q2 + 1 < 11) r[2 * q2 + 1] = acc.y;
         }
       }
       const double cnt = LEAN ? (double)n : r[10];
@@ -1939,6 +2001,10 @@ int launch_pair_kernel(const b200icp_problem* prob, const LaunchShape& ls, Kerne
   const int S = dense ? kPairDenseS : kPairS;
   args.ncap = (prob->src_pitch + 32 * S - 1) / (32 * S) * (32 * S);
   args.passes = args.ncap / (32 * S);
+  if (args.passes > kPairMaxPasses) {
+    set_error("source pitch exceeds the pair kernel's pass table");
+    return B200ICP_ERR_UNSUPPORTED_SHAPE;
+  }
   LaunchShape ps = ls;
   // W follows the 64-source blocks of the float64 phase, not the pass width of the search, so that
   // the dense and the pruned kernel add the sums in the same order (bit-identical results)
@@ -1968,6 +2034,10 @@ int launch_nn_warp_kernel(const b200icp_problem* prob, const LaunchShape& ls, Ke
   const int S = dense ? kPairDenseS : kPairS;
   args.ncap = (prob->src_pitch + 32 * S - 1) / (32 * S) * (32 * S);
   args.passes = args.ncap / (32 * S);
+  if (args.passes > kPairMaxPasses) {
+    set_error("source pitch exceeds the pair kernel's pass table");
+    return B200ICP_ERR_UNSUPPORTED_SHAPE;
+  }
   LaunchShape ps = ls;
   ps.warps = 1;
   ps.smem = pair_tile_bytes(ls.mcap, args.ncap, args.passes, 1);
