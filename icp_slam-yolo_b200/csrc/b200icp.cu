@@ -1311,16 +1311,23 @@ icp_align_pair_kernel(const KernelArgs a) {      // (the dense sweep holds 6 sou
       // every sweep also yields the bounds of the reuse (the two-group budget usually survives even
       // the large moves of the first iterations)
       const bool track = a.reuse != 0;
-      for (int pass = warp; pass < a.passes; pass += W) {
+      // which of this warp's passes need a search: one threshold per lane, one ballot (a pass is
+      // searched and its thresholds are written by the same warp in every iteration)
+      const float cm = __double2float_ru(cum_move);
+      unsigned need;
+      {
+        const bool own = lane < a.passes && lane % W == warp && lane * (32 * SC) < n;
+        need = __ballot_sync(kFull, own && !(track && cm <= t.tnn[own ? lane : 0]));
+      }
+      while (need) {
+        const int pass = __ffs(need) - 1;
+        need &= need - 1;
         const int base = pass * 32 * SC;
-        if (base >= n) break;
-        const float cm = __double2float_ru(cum_move);
-        if (a.reuse != 0 && cm <= t.tnn[pass]) continue;                   // nearest neighbours provably unchanged
-        const bool reuse_grp = a.reuse != 0 && cm <= t.tgrp[pass];
+        const bool reuse_grp = track && cm <= t.tgrp[pass];
         float bud_grp, bud_nn;
         evals += pair_search_pass<SC, PRUNE>(t, base, n, m, lane, reuse_grp, track, bud_grp, bud_nn);
-        if (a.reuse != 0 && lane == 0) {
-          if (track && !reuse_grp)
+        if (track && lane == 0) {
+          if (!reuse_grp)
             t.tgrp[pass] = bud_grp > 0.f ? __double2float_rd(cum_move + 0.999 * (double)bud_grp) : -CUDART_INF_F;
           t.tnn[pass] = bud_nn > 0.f ? fminf(t.tgrp[pass], __double2float_rd(cum_move + 0.999 * (double)bud_nn))
                                      : -CUDART_INF_F;
