@@ -34,7 +34,7 @@ def sass_rows(rep):
 
 def line_map(kernel_substr):
     tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "icp_slam-yolo_b200", "lib", "libb200icp.so")],
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("B200ICP_LIB", os.path.join(ROOT, "icp_slam-yolo_b200", "lib", "libb200icp.so"))],
                    cwd=tmp, capture_output=True)
     for f in sorted(os.listdir(tmp)):
         if not f.endswith(".cubin"):
