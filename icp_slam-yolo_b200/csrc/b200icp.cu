@@ -1041,8 +1041,8 @@ __device__ __forceinline__ void pair_stage_targets(PairTile& t, int tid, int lan
 }
 
 // The exact decision inside the (up to) two candidate groups of a source: FP32 direct-difference
-// distances of their 16 targets, the 4-bit slot packed into the low mantissa bits (relative
-// perturbation <= 2^-19, inside the guard), so the argmin and the runner-up are plain min/max
+// distances of their 16 targets, the slot number packed into the low mantissa byte (relative
+// perturbation <= 2^-15, covered by kUpD), so the argmin and the runner-up are plain min/max
 // chains.  Returns the winning slot (0..7: group ga, 8..15: group gb), whether a runner-up lies
 // inside the FP32 guard band (-> float64 rescan), `ubd` >= the exact distance from the source to
 // the winner and `los` <= the exact distance to every other target of the two groups.
@@ -1074,9 +1074,13 @@ __device__ __forceinline__ int in_group_decide(const WarpTile& t, int ga, int gb
     const float2 d45 = __ffma2_rn(v2, v2, __fmul2_rn(u2, u2)), d67 = __ffma2_rn(v3, v3, __fmul2_rn(u3, u3));
     const float ds[8] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y, d67.x, d67.y};   // sentinels: ~2e36
     unsigned key[8];
+    // one PRMT per key: the slot number replaces the low mantissa BYTE (two registers hold the eight
+    // slot bytes; the group bit is or-ed into the two survivors of the group's tournament).  d >= 0:
+    // the bit patterns are ordered like the values
+    const unsigned slots_lo = 0x03020100u, slots_hi = 0x07060504u;
 #pragma unroll
     for (int u = 0; u < kGroup; ++u)
-      key[u] = (__float_as_uint(ds[u]) & ~15u) | (unsigned)(8 * h + u);             // d >= 0: bits are ordered
+      key[u] = __byte_perm(__float_as_uint(ds[u]), u < 4 ? slots_lo : slots_hi, 0x3214u + (unsigned)(u & 3));
     // tournament instead of a 16-long dependent min/max chain: 17 operations per group, depth 4
     unsigned lo[4], hi[4];
 #pragma unroll
@@ -1084,12 +1088,15 @@ __device__ __forceinline__ int in_group_decide(const WarpTile& t, int ga, int gb
     merge_two_smallest(lo[0], hi[0], lo[1], hi[1]);
     merge_two_smallest(lo[2], hi[2], lo[3], hi[3]);
     merge_two_smallest(lo[0], hi[0], lo[2], hi[2]);
+    if (h == 1) { lo[0] |= 8u; hi[0] |= 8u; }
     merge_two_smallest(best, second, lo[0], hi[0]);
   }
-  const float bd = __uint_as_float(best & ~15u), sd = __uint_as_float(second & ~15u);
+  // the keys lost their low mantissa byte: d^2 is known to 2^-15, d to 2^-16 (1.53e-5) relative
+  const float bd = __uint_as_float(best & ~255u), sd = __uint_as_float(second & ~255u);
+  constexpr float kUpD = 1.00002f;
   const float cs = fmaxf(fabsf(fx), fabsf(fy));
   const float guard = (cs + t.tmax) * 4.76837158e-7f;                // 2^-21 (cs + tmax)
-  ubd = sqrtf(bd) * 1.000004f + guard;
+  ubd = sqrtf(bd) * kUpD + guard;
   near_tie = sd <= ubd * ubd * 1.000001f;
   los = sqrtf(sd) * 0.999996f - guard;
   return (int)(best & 15u);

@@ -47,9 +47,28 @@ void b200icp_set_error_str(const char* msg);   // defined in b200icp.cu
 
 namespace {
 
-constexpr int kChunk = 1024;          // map points per bounding circle
+#ifndef S2M_CHUNK
+#define S2M_CHUNK 1024
+#endif
+constexpr int kChunk = S2M_CHUNK;     // map points per bounding circle
 constexpr int kSuper = 32;            // chunks per second-level circle (one lane each)
-constexpr int kSearchWarps = 8;       // warps per CTA of the search kernel
+#ifndef S2M_SEARCH_WARPS
+#define S2M_SEARCH_WARPS 8
+#endif
+#ifndef S2M_MIN_BLOCKS
+#define S2M_MIN_BLOCKS 4               // 64 registers: 32 resident warps per SM (the kernel is latency-bound)
+#endif
+#ifndef S2M_FILTER_FROM_UB
+#define S2M_FILTER_FROM_UB 1
+#endif
+#ifndef S2M_TRIP_UNROLL
+#define S2M_TRIP_UNROLL 1
+#endif
+#ifndef S2M_FP32_FILTER
+#define S2M_FP32_FILTER 1
+#endif
+constexpr int kTripUnroll = S2M_TRIP_UNROLL;
+constexpr int kSearchWarps = S2M_SEARCH_WARPS;   // warps per CTA of the search kernel
 constexpr int kUpdateThreads = 256;
 constexpr int kMaxUpdateCtas = 64;
 constexpr int kMaxWorld = 32;
@@ -335,19 +354,41 @@ __device__ __forceinline__ bool circle_hit(const Circle& c, double sx, double sy
 }
 
 // Exhaustive float64 scan of one chunk for one point: lanes stride over the chunk, eight
-// independent loads in flight per lane, strict < in ascending index per lane.
-// (bd, bp): best squared distance and its position in the scanned array.  Strict < in ascending
-// position keeps the lowest position on exact ties, which is the lowest ORIGINAL index when the map
-// is scanned in its given order; in a Morton-sorted copy exact ties are re-decided on order[].
+// independent loads in flight per lane.
+// (bd, bp): best squared distance and its position in the scanned array.  On exact ties the lowest
+// ORIGINAL index wins whatever the order the chunks are scanned in (the closest chunk goes first):
+// the position itself when the map is scanned in its given order, order[] in a Morton-sorted copy.
 __device__ __forceinline__ void consider(const SearchArgs& a, double d, long long pos, double& bd, long long& bp) {
   if (d <= bd) {
     if (d < bd) { bd = d; bp = pos; }
-    else if (a.order && bp != kNoIndex && a.order[pos] < a.order[bp]) bp = pos;
+    else if (bp != kNoIndex && (a.order ? a.order[pos] < a.order[bp] : pos < bp)) bp = pos;   // exact tie
   }
 }
 
+// FP32 filter in front of the exact float64 test (float32 maps).  A map point can only change the
+// result if its exact distance is <= the best so far.  With s32 = RN(s) and the float32 point q
+// (exact), the FP32 value d32 = RN(dx^2 + dy^2), dx = RN(q.x - s32.x), carries a relative error
+// < 2^-21 in the distance plus the absolute error of rounding s: |s - s32| <= 2^-24 (|s.x| + |s.y|)
+// per axis.  So  dist >= sqrt(d32) (1 - 2^-21) - A,  A = 5e-7 (|s.x| + |s.y|) + 1e-20  (more than 4 x
+// the rounding of s), and every point with  d32 > thr = RU(((sqrt(best) + A) * 1.000004)^2)  is PROVEN
+// farther than the best: it is skipped without the two conversions and five float64 operations of
+// the exact test.  Points that pass go through `consider` unchanged, so the result is bit for bit the
+// one of the unfiltered scan.  `best` may be the best of the WHOLE warp (another lane's point at
+// exactly that distance still passes: d <= best).
+struct Fp32Filter {
+  float sx, sy;      // RN(s)
+  float thr;         // skip threshold on d32 (+inf: no bound yet)
+  double slack;      // A
+};
+
+__device__ __forceinline__ float filter_threshold(double best, double slack) {
+  if (!(best < CUDART_INF)) return CUDART_INF_F;
+  const double r = (sqrt(best) + slack) * 1.000004;
+  return __double2float_ru(r * r);
+}
+
 __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double sx, double sy, int lane,
-                                           double& bd, long long& bp) {
+                                           double& bd, long long& bp, Fp32Filter& f) {
   const int64_t j0 = (int64_t)lc * kChunk;
   const int cnt = (int)min((int64_t)kChunk, a.m - j0);
   int j = lane;
@@ -357,9 +398,28 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
       float2 q[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) q[u] = __ldg(p + j + 32 * u);
+#if S2M_FP32_FILTER
+      float d32[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float dx = q[u].x - f.sx, dy = q[u].y - f.sy;
+        d32[u] = fmaf(dx, dx, dy * dy);
+      }
+      const float lo = fminf(fminf(fminf(d32[0], d32[1]), fminf(d32[2], d32[3])),
+                             fminf(fminf(d32[4], d32[5]), fminf(d32[6], d32[7])));
+      if (lo <= f.thr) {                      // rare once the closest chunk has been scanned
+        const double before = bd;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (d32[u] <= f.thr)
+            consider(a, dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y)), j0 + j + 32 * u, bd, bp);
+        if (bd < before) f.thr = fminf(f.thr, filter_threshold(bd, f.slack));
+      }
+#else
 #pragma unroll
       for (int u = 0; u < 8; ++u)
         consider(a, dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y)), j0 + j + 32 * u, bd, bp);
+#endif
     }
   } else {
     const double2* __restrict__ p = reinterpret_cast<const double2*>(a.points) + j0;
@@ -375,9 +435,11 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
 }
 
 constexpr int kSuperBlock = 1024;     // super-chunks per traversal block: one candidate bit per lane and trip
+constexpr int kListCap = 64;          // listed candidate chunks per scan point (more: second traversal)
 
-__global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_kernel(const SearchArgs a) {
   __shared__ __align__(16) b200icp_s2m_record srec[kSearchWarps];     // the CTA's records, staged for the peer stores
+  __shared__ int clist[kSearchWarps][kListCap];                       // per warp: the chunks within reach of its point
   b200icp_s2m_state* st = a.state;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -433,17 +495,110 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
       }
       ub = warp_min_f64(ub1) * kUp;
     }
-    // ---- (3) exact float64 scan of every local chunk within reach.  Two traversals of the local
-    // circles: the first finds the chunk whose centre is closest; if the bound is wider than that
-    // chunk (the scan moved a lot, or this is the first iteration) the chunk is scanned first and
-    // its best distance becomes the bound.  The second scans every chunk within the bound, ascending.
+    // ---- (3) exact float64 scan of every local chunk within reach.  ONE traversal of the local
+    // circles lists the chunks within the bound (ascending, per-warp list in shared memory) and
+    // finds the one whose centre is closest.  That chunk is scanned first; if the bound was wider
+    // than it (the scan moved a lot, or this is the first iteration) its best distance becomes the
+    // bound and the listed chunks are re-tested against it -- the same predicate on a superset, so
+    // the set of scanned chunks is exactly the one a second traversal would find.  A list that
+    // overflows (first iterations: hundreds of chunks within a loose bound) falls back to that
+    // second traversal.
     const int first_super = a.first_local_chunk / kSuper, local_supers = a.n_local_chunks / kSuper;
-    for (int phase = 0; phase < 2; ++phase) {
-      double cd = CUDART_INF, cr = 0.0;       // closest chunk centre among the candidates (phase 0)
-      int cc = -1;
+    int* const mylist = clist[warp];
+    Fp32Filter flt;
+    flt.sx = (float)s.x; flt.sy = (float)s.y;
+    flt.slack = 5e-7 * (fabs(s.x) + fabs(s.y)) + 1e-20;        // + underflow of the FP32 squares
+    // a real map point lies within ub of s (the previous nearest neighbour, or a point of the circle
+    // that gave the bound), possibly in another shard: nothing farther than ub can be the global
+    // nearest neighbour, so the filter starts from ub instead of +inf
+    flt.thr = S2M_FILTER_FROM_UB ? filter_threshold(ub * ub * kUp, flt.slack) : CUDART_INF_F;
+    int count = 0;
+    double cd = CUDART_INF, cr = 0.0;         // closest chunk centre among the candidates
+    int cc = -1;
+    for (int b0 = 0; b0 < local_supers; b0 += kSuperBlock) {
+      const int trips = (min(kSuperBlock, local_supers - b0) + 31) >> 5;
+      unsigned my = 0;                        // bit t: super b0 + 32 t + lane is within reach (loads independent)
+#pragma unroll(kTripUnroll)
+      for (int t = 0; t < trips; ++t) {
+        const int k = b0 + 32 * t + lane;
+        const bool near = k < local_supers && circle_hit(load_circle(a.super_circle, first_super + k), s.x, s.y, ub);
+        my |= (near ? 1u : 0u) << t;
+      }
+      if (!__any_sync(kFull, my != 0)) continue;
+      for (int t = 0; t < trips; ++t) {
+        unsigned smask = __ballot_sync(kFull, (my >> t) & 1u);
+        // the chunk circles of the next hit super-chunk are loaded while the current ones are tested
+        int ks = -1;
+        Circle c;
+        c.ox = 0.0; c.oy = 0.0; c.r = -1.0; c.pad = 0.0;
+        if (smask) {
+          ks = b0 + 32 * t + __ffs(smask) - 1;                         // local super-chunk
+          smask &= smask - 1;
+          c = load_circle(a.chunk_circle, (int64_t)(first_super + ks) * kSuper + lane);
+        }
+        while (ks >= 0) {
+          int kn = -1;
+          Circle cn = c;
+          if (smask) {
+            kn = b0 + 32 * t + __ffs(smask) - 1;
+            smask &= smask - 1;
+            cn = load_circle(a.chunk_circle, (int64_t)(first_super + kn) * kSuper + lane);
+          }
+          const bool hit = circle_hit(c, s.x, s.y, ub);
+          if (hit) {
+            const double dx = s.x - c.ox, dy = s.y - c.oy, d = dx * dx + dy * dy;
+            if (d < cd) { cd = d; cr = c.r; cc = ks * kSuper + lane; }
+          }
+          const unsigned cmask = __ballot_sync(kFull, hit);
+          const int at = count + __popc(cmask & ((1u << lane) - 1u));
+          if (hit && at < kListCap) mylist[at] = ks * kSuper + lane;   // ascending local chunk numbers
+          count += __popc(cmask);
+          ks = kn;
+          c = cn;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(kFull, cd, o), orr = __shfl_xor_sync(kFull, cr, o);
+      const int oc = __shfl_xor_sync(kFull, cc, o);
+      if (od < cd || (od == cd && oc >= 0 && (cc < 0 || oc < cc))) { cd = od; cr = orr; cc = oc; }
+    }
+    __syncwarp();                              // the list is read by every lane
+    if (count <= kListCap) {
+      bool tightened = false;
+      if (cc >= 0 && count > 1) {              // closest chunk first; its result is kept
+        scan_chunk(a, cc, s.x, s.y, lane, bd, bj, flt);
+        const double wbest = warp_min_f64(bd);                 // the warp's best: every lane filters on it
+        flt.thr = fminf(flt.thr, filter_threshold(wbest, flt.slack));
+        if (ub > cr) {
+          const double t2 = fmin(ub, sqrt(wbest * kUp) * kUp);
+          tightened = t2 < ub;
+          ub = t2;
+        }
+      } else {
+        cc = -1;
+      }
+      for (int e = 0; e < count; ++e) {
+        const int lc = mylist[e];
+        if (lc == cc) continue;
+        if (tightened &&
+            !circle_hit(load_circle(a.chunk_circle, (int64_t)first_super * kSuper + lc), s.x, s.y, ub)) continue;
+        scan_chunk(a, lc, s.x, s.y, lane, bd, bj, flt);
+      }
+    } else {
+      if (cc >= 0 && ub > cr) {               // the bound is wider than the closest chunk: tighten it there
+        double td = CUDART_INF;
+        long long tj = kNoIndex;
+        Fp32Filter tf = flt;
+        scan_chunk(a, cc, s.x, s.y, lane, td, tj, tf);
+        td = warp_min_f64(td);
+        flt.thr = fminf(flt.thr, filter_threshold(td, flt.slack));   // a real map point at distance td exists
+        ub = fmin(ub, sqrt(td * kUp) * kUp);
+      }
       for (int b0 = 0; b0 < local_supers; b0 += kSuperBlock) {
         const int trips = (min(kSuperBlock, local_supers - b0) + 31) >> 5;
-        unsigned my = 0;                      // bit t: super b0 + 32 t + lane is within reach (loads independent)
+        unsigned my = 0;
         for (int t = 0; t < trips; ++t) {
           const int k = b0 + 32 * t + lane;
           const bool near = k < local_supers && circle_hit(load_circle(a.super_circle, first_super + k), s.x, s.y, ub);
@@ -453,39 +608,16 @@ __global__ void __launch_bounds__(kSearchWarps * 32) s2m_search_kernel(const Sea
         for (int t = 0; t < trips; ++t) {
           unsigned smask = __ballot_sync(kFull, (my >> t) & 1u);
           while (smask) {
-            const int ks = b0 + 32 * t + __ffs(smask) - 1;             // local super-chunk
+            const int ks = b0 + 32 * t + __ffs(smask) - 1;
             smask &= smask - 1;
             const Circle c = load_circle(a.chunk_circle, (int64_t)(first_super + ks) * kSuper + lane);
-            const bool hit = circle_hit(c, s.x, s.y, ub);
-            if (phase == 0) {
-              if (hit) {
-                const double dx = s.x - c.ox, dy = s.y - c.oy, d = dx * dx + dy * dy;
-                if (d < cd) { cd = d; cr = c.r; cc = ks * kSuper + lane; }
-              }
-            } else {
-              unsigned cmask = __ballot_sync(kFull, hit);
-              while (cmask) {
-                const int lc = ks * kSuper + __ffs(cmask) - 1;           // local chunk, ascending
-                cmask &= cmask - 1;
-                scan_chunk(a, lc, s.x, s.y, lane, bd, bj);
-              }
+            unsigned cmask = __ballot_sync(kFull, circle_hit(c, s.x, s.y, ub));
+            while (cmask) {
+              const int lc = ks * kSuper + __ffs(cmask) - 1;           // local chunk, ascending
+              cmask &= cmask - 1;
+              scan_chunk(a, lc, s.x, s.y, lane, bd, bj, flt);
             }
           }
-        }
-      }
-      if (phase == 0) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double od = __shfl_xor_sync(kFull, cd, o), orr = __shfl_xor_sync(kFull, cr, o);
-          const int oc = __shfl_xor_sync(kFull, cc, o);
-          if (od < cd || (od == cd && oc >= 0 && (cc < 0 || oc < cc))) { cd = od; cr = orr; cc = oc; }
-        }
-        if (cc >= 0 && ub > cr) {             // the bound is wider than the closest chunk: tighten it there
-          double td = CUDART_INF;
-          long long tj = kNoIndex;
-          scan_chunk(a, cc, s.x, s.y, lane, td, tj);
-          td = warp_min_f64(td);
-          ub = fmin(ub, sqrt(td * kUp) * kUp);
         }
       }
     }
