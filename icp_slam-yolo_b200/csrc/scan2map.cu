@@ -3,21 +3,26 @@
 // Same reference loop as b200icp.cu (labels_segmentation/icp.py:28-53) with a target set of
 // millions of points, for the scan-to-local-map call shape of duc/ICP_LIDAR/mainn.py:297-318.
 //
-// Round-2 design: EXACT CULLING + FLOAT64 SCAN, two launches per iteration.
+// Round-2 design: EXACT CULLING + EXACT SCAN, two launches per iteration.
 //   s2m_prepare_kernel  chunks of 1,024 consecutive map points -> bounding circle (centroid,
 //                       radius); s2m_super_kernel: one circle per 32 chunks.  The circle tables
 //                       of ALL ranks are replicated on every rank (a few hundred KB), so a rank
 //                       can bound a scan point's nearest-neighbour distance over the WHOLE map
 //                       without a collective.
-//   s2m_search_kernel   one warp per scan point: (1) apply the pose increment the previous
-//                       update left pending; (2) upper bound ub of the NN distance: the distance
-//                       to the previous iteration's nearest map point (a real map point), or in
-//                       the first iteration min over circles of |s - o| + r (two levels);
-//                       (3) every LOCAL chunk whose circle comes within ub of the point is scanned
-//                       exhaustively in float64 (NumPy's operation order, strict <, ascending
-//                       index, lexicographic warp reduction): the record it emits is the exact
-//                       nearest point of this shard among all that can matter, lowest index on
-//                       ties -- no FP32 candidate stage, no ambiguity lists, no fallback scan;
+//   s2m_search_kernel   one warp per scan point, eight consecutive points per CTA: (1) apply the
+//                       pose increment the previous update left pending; (2) upper bound ub of the NN
+//                       distance: the distance to the previous iteration's nearest map point (a real
+//                       map point), or in the first iteration min over circles of |s - o| + r (two
+//                       levels); (2b) the CTA tests the local super-circles once against a ball that
+//                       holds the reach circles of its eight points, each warp then only the
+//                       survivors; (3) ONE traversal lists every LOCAL chunk whose circle comes within
+//                       ub of the point (per-warp list in shared memory); the chunk with the closest
+//                       centre is scanned first and tightens the bound, the rest are re-tested and
+//                       scanned: exhaustively, behind an exact FP32 filter that skips the points PROVEN
+//                       farther than the bound, the survivors in float64 (NumPy's operation order;
+//                       exact ties go to the lowest original index, lexicographic warp reduction): the
+//                       record it emits is the exact nearest point of this shard among all that can
+//                       matter -- no approximate candidate stage, no ambiguity lists, no fallback scan;
 //                       (4) the 32-byte record is stored straight into EVERY rank's inbox over
 //                       NVLink (peer stores) and the last CTA raises this rank's flag there
 //                       (system-scope release): the all-gather is the kernel's epilogue.
@@ -47,28 +52,11 @@ void b200icp_set_error_str(const char* msg);   // defined in b200icp.cu
 
 namespace {
 
-#ifndef S2M_CHUNK
-#define S2M_CHUNK 1024
-#endif
-constexpr int kChunk = S2M_CHUNK;     // map points per bounding circle
+constexpr int kChunk = 1024;          // map points per bounding circle (512: 2.53 ms, 2048: 2.49 ms against 2.33 ms per alignment)
 constexpr int kSuper = 32;            // chunks per second-level circle (one lane each)
-#ifndef S2M_SEARCH_WARPS
-#define S2M_SEARCH_WARPS 8
-#endif
-#ifndef S2M_MIN_BLOCKS
-#define S2M_MIN_BLOCKS 4               // 64 registers: 32 resident warps per SM (the kernel is latency-bound)
-#endif
-#ifndef S2M_FILTER_FROM_UB
-#define S2M_FILTER_FROM_UB 1
-#endif
-#ifndef S2M_TRIP_UNROLL
-#define S2M_TRIP_UNROLL 1
-#endif
-#ifndef S2M_FP32_FILTER
-#define S2M_FP32_FILTER 1
-#endif
-constexpr int kTripUnroll = S2M_TRIP_UNROLL;
-constexpr int kSearchWarps = S2M_SEARCH_WARPS;   // warps per CTA of the search kernel
+constexpr int kSearchWarps = 8;       // warps per CTA of the search kernel
+constexpr int kSearchMinCtas = 4;     // 64 registers: 32 resident warps per SM (the kernel is latency-bound:
+                                      // 80 registers / 24 warps costs 40 %)
 constexpr int kUpdateThreads = 256;
 constexpr int kMaxUpdateCtas = 64;
 constexpr int kMaxWorld = 32;
@@ -387,6 +375,27 @@ __device__ __forceinline__ float filter_threshold(double best, double slack) {
   return __double2float_ru(r * r);
 }
 
+// Eight points of one lane (positions pos0 + 32 u) against the point (sx, sy).
+__device__ __forceinline__ void scan_round(const SearchArgs& a, const float2 (&q)[8], int64_t pos0, double sx,
+                                           double sy, double& bd, long long& bp, Fp32Filter& f) {
+  float d32[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float dx = q[u].x - f.sx, dy = q[u].y - f.sy;
+    d32[u] = fmaf(dx, dx, dy * dy);
+  }
+  const float lo = fminf(fminf(fminf(d32[0], d32[1]), fminf(d32[2], d32[3])),
+                         fminf(fminf(d32[4], d32[5]), fminf(d32[6], d32[7])));
+  if (lo <= f.thr) {                          // rare: the filter starts from the bound of the NN distance
+    const double before = bd;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (d32[u] <= f.thr)
+        consider(a, dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y)), pos0 + 32 * u, bd, bp);
+    if (bd < before) f.thr = fminf(f.thr, filter_threshold(bd, f.slack));
+  }
+}
+
 __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double sx, double sy, int lane,
                                            double& bd, long long& bp, Fp32Filter& f) {
   const int64_t j0 = (int64_t)lc * kChunk;
@@ -398,28 +407,7 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
       float2 q[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) q[u] = __ldg(p + j + 32 * u);
-#if S2M_FP32_FILTER
-      float d32[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float dx = q[u].x - f.sx, dy = q[u].y - f.sy;
-        d32[u] = fmaf(dx, dx, dy * dy);
-      }
-      const float lo = fminf(fminf(fminf(d32[0], d32[1]), fminf(d32[2], d32[3])),
-                             fminf(fminf(d32[4], d32[5]), fminf(d32[6], d32[7])));
-      if (lo <= f.thr) {                      // rare once the closest chunk has been scanned
-        const double before = bd;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (d32[u] <= f.thr)
-            consider(a, dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y)), j0 + j + 32 * u, bd, bp);
-        if (bd < before) f.thr = fminf(f.thr, filter_threshold(bd, f.slack));
-      }
-#else
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        consider(a, dist2_f64(sx, sy, make_double2((double)q[u].x, (double)q[u].y)), j0 + j + 32 * u, bd, bp);
-#endif
+      scan_round(a, q, j0 + j, sx, sy, bd, bp, f);
     }
   } else {
     const double2* __restrict__ p = reinterpret_cast<const double2*>(a.points) + j0;
@@ -436,10 +424,29 @@ __device__ __forceinline__ void scan_chunk(const SearchArgs& a, int lc, double s
 
 constexpr int kSuperBlock = 1024;     // super-chunks per traversal block: one candidate bit per lane and trip
 constexpr int kListCap = 64;          // listed candidate chunks per scan point (more: second traversal)
+constexpr int kSupCap = 64;           // super-chunks the CTA's ball may meet (more: per-warp traversal of all)
+#ifndef S2M_TIMING
+#define S2M_TIMING 0
+#endif
+#if S2M_TIMING
+__device__ unsigned long long g_s2m_clk[8];   // debug builds only: per-phase cycles summed over warps
+#define S2M_TICK(slot)                                                          \
+  do {                                                                          \
+    const long long now_ = clock64();                                           \
+    if (lane == 0) atomicAdd(&g_s2m_clk[slot], (unsigned long long)(now_ - tick_)); \
+    tick_ = now_;                                                               \
+  } while (0)
+#else
+#define S2M_TICK(slot) do { } while (0)
+#endif
 
-__global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(kSearchWarps * 32, kSearchMinCtas) s2m_search_kernel(const SearchArgs a) {
   __shared__ __align__(16) b200icp_s2m_record srec[kSearchWarps];     // the CTA's records, staged for the peer stores
   __shared__ int clist[kSearchWarps][kListCap];                       // per warp: the chunks within reach of its point
+  __shared__ double2 cta_pt[kSearchWarps];                            // the CTA's points and bounds
+  __shared__ double cta_ub[kSearchWarps];
+  __shared__ int sup_list[kSupCap];                                   // local super-chunks within reach of the CTA
+  __shared__ int sup_count;
   b200icp_s2m_state* st = a.state;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -455,16 +462,25 @@ __global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_
     seq = *(inbox_flags(a.peers[a.rank], a.world, a.n) + 2 * a.world) + 1;   // exchange counter of this rank
     slot = (int)(seq & 1);
   }
+#if S2M_TIMING
+  long long tick_ = clock64();
+#endif
   double bd = CUDART_INF;
   long long bj = kNoIndex;
+  double2 s = make_double2(0.0, 0.0);
+  double ub = 0.0, cd = CUDART_INF, cr = 0.0;   // bound of the NN distance; closest chunk centre among the candidates
+  int cc = -1, count = 0;
+  Fp32Filter flt;
+  flt.sx = 0.f; flt.sy = 0.f; flt.thr = CUDART_INF_F; flt.slack = 0.0;
+  int* const mylist = clist[warp];
+  const int first_super = a.first_local_chunk / kSuper, local_supers = a.n_local_chunks / kSuper;
   if (active) {
-    double2 s = make_double2(a.src64[2 * i], a.src64[2 * i + 1]);
+    s = make_double2(a.src64[2 * i], a.src64[2 * i + 1]);
     if (pending) {
       s = apply_pending(st, s);
       if (lane == 0) { a.src64[2 * i] = s.x; a.src64[2 * i + 1] = s.y; }
     }
     // ---- (2) upper bound of the nearest-neighbour distance over the whole map
-    double ub;
     const double px = a.prev_nn ? a.prev_nn[2 * i] : CUDART_NAN, py = a.prev_nn ? a.prev_nn[2 * i + 1] : CUDART_NAN;
     if (px == px) {
       ub = sqrt(dist2_f64(s.x, s.y, make_double2(px, py)) * kUp) * kUp;
@@ -495,6 +511,43 @@ __global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_
       }
       ub = warp_min_f64(ub1) * kUp;
     }
+  }
+  // ---- (2b) the eight points of a CTA are neighbours on the scan, so their reach circles nearly
+  // coincide: the CTA tests the local super-circles ONCE against a ball that contains all eight
+  // (centre = the first point, radius = max_w(|s_w - s_0| + ub_w)) -- 256 threads, one or two
+  // circles each -- and every warp then tests only the few survivors with its own (s, ub).  A
+  // super-circle within reach of point w is within reach of the ball (triangle inequality), so the
+  // per-warp hit sets are unchanged.  More survivors than the list holds (first iteration): every
+  // warp walks all super-circles itself as before.
+  int nsup = -1;                               // -1: no CTA list
+  {
+    if (lane == 0) {
+      cta_pt[warp] = make_double2(s.x, s.y);
+      cta_ub[warp] = active ? ub : -1.0;
+    }
+    if (threadIdx.x == 0) sup_count = 0;
+    __syncthreads();
+    const double2 c0 = cta_pt[0];              // warp 0 of a launched CTA always has a point
+    double R = 0.0;
+#pragma unroll
+    for (int w = 0; w < kSearchWarps; ++w) {
+      const double ubw = cta_ub[w];
+      if (ubw >= 0.0) {
+        const double dx = cta_pt[w].x - c0.x, dy = cta_pt[w].y - c0.y;
+        R = fmax(R, sqrt(dx * dx + dy * dy) * kUp + ubw);
+      }
+    }
+    R *= kUp;
+    for (int k = threadIdx.x; k < local_supers; k += kSearchWarps * 32) {
+      if (circle_hit(load_circle(a.super_circle, first_super + k), c0.x, c0.y, R)) {
+        const int at = atomicAdd(&sup_count, 1);
+        if (at < kSupCap) sup_list[at] = k;
+      }
+    }
+    __syncthreads();
+    nsup = sup_count <= kSupCap ? sup_count : -1;
+  }
+  if (active) {
     // ---- (3) exact float64 scan of every local chunk within reach.  ONE traversal of the local
     // circles lists the chunks within the bound (ascending, per-warp list in shared memory) and
     // finds the one whose centre is closest.  That chunk is scanned first; if the bound was wider
@@ -503,59 +556,63 @@ __global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_
     // the set of scanned chunks is exactly the one a second traversal would find.  A list that
     // overflows (first iterations: hundreds of chunks within a loose bound) falls back to that
     // second traversal.
-    const int first_super = a.first_local_chunk / kSuper, local_supers = a.n_local_chunks / kSuper;
-    int* const mylist = clist[warp];
-    Fp32Filter flt;
+    S2M_TICK(0);                               // point, pending increment, bound
     flt.sx = (float)s.x; flt.sy = (float)s.y;
     flt.slack = 5e-7 * (fabs(s.x) + fabs(s.y)) + 1e-20;        // + underflow of the FP32 squares
     // a real map point lies within ub of s (the previous nearest neighbour, or a point of the circle
     // that gave the bound), possibly in another shard: nothing farther than ub can be the global
     // nearest neighbour, so the filter starts from ub instead of +inf
-    flt.thr = S2M_FILTER_FROM_UB ? filter_threshold(ub * ub * kUp, flt.slack) : CUDART_INF_F;
-    int count = 0;
-    double cd = CUDART_INF, cr = 0.0;         // closest chunk centre among the candidates
-    int cc = -1;
-    for (int b0 = 0; b0 < local_supers; b0 += kSuperBlock) {
-      const int trips = (min(kSuperBlock, local_supers - b0) + 31) >> 5;
-      unsigned my = 0;                        // bit t: super b0 + 32 t + lane is within reach (loads independent)
-#pragma unroll(kTripUnroll)
-      for (int t = 0; t < trips; ++t) {
-        const int k = b0 + 32 * t + lane;
-        const bool near = k < local_supers && circle_hit(load_circle(a.super_circle, first_super + k), s.x, s.y, ub);
-        my |= (near ? 1u : 0u) << t;
+    flt.thr = filter_threshold(ub * ub * kUp, flt.slack);
+    // chunk level: the 32 chunk circles of every hit super-chunk, one per lane; the circles of the
+    // next hit super-chunk are loaded while the current ones are tested
+    auto visit = [&](unsigned smask, auto super_of) {
+      int ks = -1;
+      Circle c;
+      c.ox = 0.0; c.oy = 0.0; c.r = -1.0; c.pad = 0.0;
+      if (smask) {
+        ks = super_of(__ffs(smask) - 1);                               // local super-chunk
+        smask &= smask - 1;
+        c = load_circle(a.chunk_circle, (int64_t)(first_super + ks) * kSuper + lane);
       }
-      if (!__any_sync(kFull, my != 0)) continue;
-      for (int t = 0; t < trips; ++t) {
-        unsigned smask = __ballot_sync(kFull, (my >> t) & 1u);
-        // the chunk circles of the next hit super-chunk are loaded while the current ones are tested
-        int ks = -1;
-        Circle c;
-        c.ox = 0.0; c.oy = 0.0; c.r = -1.0; c.pad = 0.0;
+      while (ks >= 0) {
+        int kn = -1;
+        Circle cn = c;
         if (smask) {
-          ks = b0 + 32 * t + __ffs(smask) - 1;                         // local super-chunk
+          kn = super_of(__ffs(smask) - 1);
           smask &= smask - 1;
-          c = load_circle(a.chunk_circle, (int64_t)(first_super + ks) * kSuper + lane);
+          cn = load_circle(a.chunk_circle, (int64_t)(first_super + kn) * kSuper + lane);
         }
-        while (ks >= 0) {
-          int kn = -1;
-          Circle cn = c;
-          if (smask) {
-            kn = b0 + 32 * t + __ffs(smask) - 1;
-            smask &= smask - 1;
-            cn = load_circle(a.chunk_circle, (int64_t)(first_super + kn) * kSuper + lane);
-          }
-          const bool hit = circle_hit(c, s.x, s.y, ub);
-          if (hit) {
-            const double dx = s.x - c.ox, dy = s.y - c.oy, d = dx * dx + dy * dy;
-            if (d < cd) { cd = d; cr = c.r; cc = ks * kSuper + lane; }
-          }
-          const unsigned cmask = __ballot_sync(kFull, hit);
-          const int at = count + __popc(cmask & ((1u << lane) - 1u));
-          if (hit && at < kListCap) mylist[at] = ks * kSuper + lane;   // ascending local chunk numbers
-          count += __popc(cmask);
-          ks = kn;
-          c = cn;
+        const bool hit = circle_hit(c, s.x, s.y, ub);
+        if (hit) {
+          const double dx = s.x - c.ox, dy = s.y - c.oy, d = dx * dx + dy * dy;
+          if (d < cd) { cd = d; cr = c.r; cc = ks * kSuper + lane; }
         }
+        const unsigned cmask = __ballot_sync(kFull, hit);
+        const int at = count + __popc(cmask & ((1u << lane) - 1u));
+        if (hit && at < kListCap) mylist[at] = ks * kSuper + lane;
+        count += __popc(cmask);
+        ks = kn;
+        c = cn;
+      }
+    };
+    if (nsup >= 0) {                           // the CTA's survivors (any order: ties are decided on positions)
+      for (int q0 = 0; q0 < nsup; q0 += 32) {
+        const int k = q0 + lane < nsup ? sup_list[q0 + lane] : -1;
+        const bool near = k >= 0 && circle_hit(load_circle(a.super_circle, first_super + k), s.x, s.y, ub);
+        visit(__ballot_sync(kFull, near), [&](int bit) { return sup_list[q0 + bit]; });
+      }
+    } else {
+      for (int b0 = 0; b0 < local_supers; b0 += kSuperBlock) {
+        const int trips = (min(kSuperBlock, local_supers - b0) + 31) >> 5;
+        unsigned my = 0;                      // bit t: super b0 + 32 t + lane is within reach (loads independent)
+        for (int t = 0; t < trips; ++t) {
+          const int k = b0 + 32 * t + lane;
+          const bool near = k < local_supers && circle_hit(load_circle(a.super_circle, first_super + k), s.x, s.y, ub);
+          my |= (near ? 1u : 0u) << t;
+        }
+        if (!__any_sync(kFull, my != 0)) continue;
+        for (int t = 0; t < trips; ++t)
+          visit(__ballot_sync(kFull, (my >> t) & 1u), [&](int bit) { return b0 + 32 * t + bit; });
       }
     }
 #pragma unroll
@@ -565,6 +622,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_
       if (od < cd || (od == cd && oc >= 0 && (cc < 0 || oc < cc))) { cd = od; cr = orr; cc = oc; }
     }
     __syncwarp();                              // the list is read by every lane
+    S2M_TICK(1);                               // traversal
+  }
+  if (active) {
     if (count <= kListCap) {
       bool tightened = false;
       if (cc >= 0 && count > 1) {              // closest chunk first; its result is kept
@@ -621,6 +681,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_
         }
       }
     }
+  }
+  S2M_TICK(2);                                 // scans
+  if (active) {
     long long bo = (bj != kNoIndex && a.order) ? (long long)a.order[bj] : bj;   // original local index
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {                       // lexicographic (distance, original index)
@@ -652,10 +715,12 @@ __global__ void __launch_bounds__(kSearchWarps * 32, S2M_MIN_BLOCKS) s2m_search_
       if (lane < words) dst[lane] = reinterpret_cast<const double*>(srec)[lane];
     }
   }
+  S2M_TICK(3);                                 // record, peer stores
   // last CTA: the pending increment is applied everywhere; raise this rank's flag on every rank.
   // One system-scope fence per CTA (after the barrier: cumulative over the stores of all its warps)
   // orders the records before the ticket, the ticket chain before the last CTA's fence and flag.
   __syncthreads();
+  S2M_TICK(4);                                 // wait for the CTA's slowest warp
   if (threadIdx.x == 0) {
     if (a.peers) __threadfence_system(); else __threadfence();
     const unsigned ticket = atomicAdd(a.scratch + kTicketSearch, 1u);
@@ -1019,5 +1084,15 @@ int b200icp_peer_free(void* ptr) {
   if (ptr && cudaFree(ptr) != cudaSuccess) return cuda_check("cudaFree");
   return B200ICP_OK;
 }
+
+#if S2M_TIMING
+// debug builds only (tools/build_variant.py ... -DS2M_TIMING=1): read and clear the phase counters
+int b200icp_s2m_debug_clocks(unsigned long long* out8) {
+  unsigned long long zero[8] = {};
+  if (cudaMemcpyFromSymbol(out8, g_s2m_clk, sizeof(zero)) != cudaSuccess) return B200ICP_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_s2m_clk, zero, sizeof(zero)) != cudaSuccess) return B200ICP_ERR_CUDA;
+  return B200ICP_OK;
+}
+#endif
 
 }  // extern "C"
