@@ -59,7 +59,10 @@ def parse():
     ap.add_argument("--map-points", type=int, default=1 << 24, help="scan2map: total map points")
     ap.add_argument("--scan-points", type=int, default=8192)
     ap.add_argument("--s2m-exchange", default="peer", choices=["peer", "nccl"])
-    ap.add_argument("--s2m-graph", action="store_true", help="scan2map: replay the 30-iteration loop as one CUDA graph")
+    ap.add_argument("--s2m-graph", dest="s2m_graph", action="store_true", default=True,
+                    help="scan2map: replay the 30-iteration loop as one CUDA graph (default with the peer exchange)")
+    ap.add_argument("--no-s2m-graph", dest="s2m_graph", action="store_false",
+                    help="scan2map: launch the 60 kernels of an alignment from the host loop")
     return ap.parse_args()
 
 
@@ -398,9 +401,11 @@ def run_b200(args):
                "h2d_only_ms": h2d_ms, "h2d_only_gbs_per_gpu": h2d / (h2d_ms * 1e-3) / 1e9,
                "host_numa": numa if numa is not None else "not bound (--no-numa-bind)",
                "limiter": ("host-to-device copy" if h2d_ms > 0.9 * e2e_ms else "kernel") +
-                          ": e2e = max(kernel, copy) + the first chunk's copy; h2d_only_ms is the copy alone with every "
-                          "rank copying at once (GPUs share host memory and PCIe uplinks)",
-               "api": "icp_slam_yolo_b200.registration.HostPipeline.run (%d chunks, copy/compute overlap)" % n_chunks}
+                          ": e2e = max(kernel + the first chunk's copy, copy + the last chunk's kernel); h2d_only_ms is "
+                          "the copy alone with every rank copying at once (GPUs share host memory and PCIe uplinks)",
+               "chunk_pairs": [int(b1 - b0) for b0, b1 in zip(pipe.bounds[:-1], pipe.bounds[1:])],
+               "api": "icp_slam_yolo_b200.registration.HostPipeline.run (largest chunk = 1/%d of the batch, ramped "
+                      "chunk sizes, copy/compute overlap)" % n_chunks}
         del pipe
 
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions
@@ -872,7 +877,11 @@ def run_scan2map(args, ctx=None):
     h_scan = torch.from_numpy(scan_np).pin_memory()
     scan = h_scan.to(dev)
     exchange = args.s2m_exchange
-    s2m = m.ScanToMap(shard, N, exchange=exchange, graph=args.s2m_graph)
+    hbm_peak, hbm_src = measured_hbm_peak()
+    s2m_ncu = ncu_summary("r2_s2m_search_ncu")
+    shard_bytes = float(e - b) * 8.0
+    use_graph = bool(args.s2m_graph) and exchange != "nccl"      # NCCL calls are not captured
+    s2m = m.ScanToMap(shard, N, exchange=exchange, graph=use_graph)
     fp32_peak = m.ffma_probe()
 
     def step():
@@ -912,18 +921,26 @@ def run_scan2map(args, ctx=None):
                    "l2": "map shard %.0f MB; a scan point touches ~7 chunks of 8 KB per iteration" % ((e - b) * 8 / 1e6),
                    "parallelism": "map sharded contiguously; %s all-gather of 32 B records per iteration (%d B per rank)" % (
                        "peer stores over NVLink in the search epilogue + flags" if (exchange == "peer" and world > 1) else ("NCCL" if world > 1 else "single rank: none"), N * 32),
-                   "cuda_graph": bool(args.s2m_graph),
+                   "cuda_graph": use_graph,
                    "final_error_mm": res.error},
         "gpu_launches": args.steps * s2m.launches,
         "per_iteration_ms": {"search": search_ms, "update_incl_peer_wait": update_ms},
-        "roofline": {"bound": "fp64", "kernel": "s2m_search_kernel",
-                     "achieved": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12, "peak": None,
-                     "unit": "TFLOP/s (brute-force-equivalent)", "frac": None,
-                     "kernel_ms": search_ms, "traffic": None, "ffma_peak_tflops": fp32_peak,
-                     "note": "achieved = brute-force-equivalent work (N_scan x M_shard x 5 FLOP per search) / time of "
-                             "one b200icp_s2m_search.  Chunks of 1,024 map points whose bounding circle is provably "
-                             "farther than a point's nearest neighbour are skipped and the rest are scanned in float64 "
-                             "(identical results), so this is not a pipe utilisation: no frac is claimed."},
+        # the search reads (almost) every chunk of the shard once per iteration -- the union of the
+        # scan points' candidate chunks covers the map -- and little else: an HBM-latency-bound kernel
+        "roofline": {"bound": "hbm", "kernel": "s2m_search_kernel",
+                     "achieved": shard_bytes / (search_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": shard_bytes / (search_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                     "algorithmic_bytes_per_launch": shard_bytes,
+                     "kernel_ms": search_ms,
+                     "traffic": (s2m_ncu or {}).get("dram_bytes") if world == 1 else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one search on ONE GPU, "
+                                       "profiles/r2_s2m_search_ncu.json (ncu --set full)" if (s2m_ncu and world == 1) else None,
+                     "brute_force_equivalent_tflops": float(N) * (e - b) * 5 / (search_ms * 1e-3) / 1e12,
+                     "ffma_peak_tflops": fp32_peak,
+                     "note": "algorithmic bytes = this rank's map shard read once per search (8 B per float32 point); "
+                             "chunks of 1,024 map points whose bounding circle is provably farther than a point's "
+                             "nearest neighbour are skipped, the rest are scanned exactly (FP32 filter + float64), so the "
+                             "brute-force-equivalent FLOP rate is a speed-up figure, not a utilisation"},
         "e2e": {"value": 1.0 / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h_scan.numel() * 4), "d2h_bytes_per_step": 136,
                 "api": "pinned host scan -> device, ScanToMap.run (map shard and circle tables resident), state -> host"},

@@ -378,8 +378,8 @@ def ffma_probe(inner_iters: int = 4096, repeats: int = 5, device="cuda") -> floa
 
 class HostPipeline:
     """End-to-end batched alignment from HOST buffers: the call a user with NumPy-side scans
-    makes.  Pinned host tables are streamed to the device in chunks on a copy stream while
-    the previous chunk's ICP kernel runs, and each chunk's poses / errors / iteration counts
+    makes.  Pinned host tables are streamed to the device in chunks (sizes: ``chunk_schedule``) on a
+    copy stream while the previous chunk's ICP kernel runs, and each chunk's poses / errors / iteration counts
     are copied back to pinned host memory, so host<->device traffic overlaps the compute.
     Consecutive chunks run on two alternating compute streams: the next chunk's CTAs fill the SMs
     that the tail wave of the current chunk leaves idle.
@@ -391,13 +391,11 @@ class HostPipeline:
                  chunks: int = 8, device="cuda"):
         self.n_pairs, self.src_pitch, self.tgt_pitch = int(n_pairs), int(src_pitch), int(tgt_pitch)
         self.device = torch.device(device)
-        self.chunk = max(1, -(-self.n_pairs // max(1, chunks)))
-        # chunk boundaries: a short first chunk (1/8 of a regular one) so that the exposed part of
-        # the pipeline -- the first host-to-device copy -- is small; the rest are regular
-        first = max(1, self.chunk // 8)
-        self.bounds = [0, min(first, self.n_pairs)]
-        while self.bounds[-1] < self.n_pairs:
-            self.bounds.append(min(self.n_pairs, self.bounds[-1] + self.chunk))
+        sizes = self.chunk_schedule(self.n_pairs, chunks)
+        self.chunk = max(sizes)
+        self.bounds = [0]
+        for sz in sizes:
+            self.bounds.append(self.bounds[-1] + sz)
         self.dtype = dtype
         c = self.chunk
         mk = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, device=self.device)
@@ -418,6 +416,35 @@ class HostPipeline:
             self.h_iters = pin(self.n_pairs, dt=torch.int32)
         self.launches = 0
         self.done_event = None
+
+    @staticmethod
+    def chunk_schedule(n_pairs: int, chunks: int = 8, growth: float = 1.25):
+        """Chunk sizes of one run.  ``chunks`` sets the LARGEST chunk (n_pairs / chunks).  Two parts of
+        the pipeline cannot be hidden: the first host-to-device copy (nothing to compute yet) and the
+        last kernel (nothing left to copy).  So the sizes ramp up geometrically from 1/8 of the largest
+        chunk -- with two staging buffers, copy i+1 starts when kernel i-1 has ended and must end before
+        kernel i does, which holds while the chunks grow by no more than the kernel / copy time ratio
+        (1.3 on the headline workload; a regular second chunk after a short first one left the GPU idle
+        for 0.7 ms of a 9.8 ms step) -- and the run ends with two shrinking chunks (1/2 and 1/4 of the
+        largest), which is what a copy-bound run (several GPUs sharing the host's memory bandwidth)
+        exposes after its last copy."""
+        n_pairs, chunks = int(n_pairs), max(1, int(chunks))
+        if chunks == 1:
+            return [n_pairs]
+        big = max(1, -(-n_pairs // chunks))
+        tail = [t for t in (big // 2, big // 4) if t >= 1]
+        avail = n_pairs - sum(tail)
+        if avail <= 0:
+            tail, avail = [], n_pairs
+        head, sz = [], max(1.0, big / 8.0)
+        while int(sz) < big and sum(head) + int(sz) <= avail:
+            head.append(int(sz))
+            sz *= growth
+        rest = avail - sum(head)
+        body = [big] * (rest // big)
+        if rest % big:                    # the remainder joins the shrinking end of the run
+            tail = sorted(tail + [rest % big], reverse=True)
+        return head + body + tail
 
     def bytes_per_run(self, ragged: bool):
         elt = 4 if self.dtype == torch.float32 else 8

@@ -203,3 +203,24 @@ def test_hostmem_topology_parsing_and_binding(pkg, tmp_path, monkeypatch):
     (sysfs / "devices/system/node/online").write_text("0\n")
     with hm.near_gpu(0, sysfs=str(sysfs)) as rec:
         assert not rec["bound"] and rec["why"] == "single NUMA node"
+
+
+def test_host_pipeline_chunk_schedule(pkg):
+    """HostPipeline's chunk sizes: cover the batch exactly, never exceed the staging buffers, ramp up
+    by at most the growth factor from a short first chunk (the first copy is exposed) and end with
+    shrinking chunks (the last kernel is exposed)."""
+    from icp_slam_yolo_b200.registration import HostPipeline
+    for n in (1, 2, 5, 100, 1830, 8192, 65536, 65537, 1 << 20):
+        for chunks in (1, 2, 4, 8, 16):
+            sizes = HostPipeline.chunk_schedule(n, chunks)
+            big = max(1, -(-n // chunks))
+            assert sum(sizes) == n and min(sizes) >= 1 and max(sizes) <= big, (n, chunks, sizes)
+            if chunks == 1:
+                assert sizes == [n]
+    sizes = HostPipeline.chunk_schedule(65536, 8)
+    big = 8192
+    assert sizes[0] == big // 8 and sizes[-1] <= big // 4
+    peak = sizes.index(big)
+    for a, b in zip(sizes[:peak], sizes[1:peak + 1]):
+        assert b <= int(a * 1.25) + 1 or b == big and a * 1.25 >= big * 0.9, (a, b)
+    assert sizes[peak:] == sorted(sizes[peak:], reverse=True)

@@ -145,3 +145,32 @@ def test_scan_to_map_spatial_sort_makes_unordered_maps_cullable(b200):
     b = b200.scan_to_map_icp(torch.from_numpy(scan).cuda(), b200.MapShard(torch.from_numpy(ordered).cuda(), spatial_sort=False),
                              6, -1.0, want_indices=True)
     assert torch.equal(a.indices, b.indices) and a.error == b.error and np.array_equal(a.R, b.R)
+
+
+def test_scan_to_map_ties_in_given_order_closest_chunk_first(b200):
+    """Exact duplicates INSIDE one shard, in different chunks of a map scanned in its given order.
+    The search scans the chunk with the closest centre first and the others in the order the CTA's
+    super-circle pass left them, so the tie rule (lowest original index) must not depend on the
+    scanning order; and from the second iteration on the FP32 filter starts from the distance to the
+    previous nearest neighbour, which every duplicate of that point must pass."""
+    wall = orc.synth_map(24000, dtype=np.float32)
+    a, b = wall[:9000], wall[9000:24000]
+    # the copy of `a` starts at index 24000 - not a multiple of the 1,024-point chunk relative to `a`
+    # (9000 + 15000 = 24000 = 23 chunks + 448): its chunks, circles and centres differ from the original's
+    map_pts = np.concatenate([a, b, a]).astype(np.float32)
+    scan = orc.synth_scan_for_map(1500, dtype=np.float32)
+    o = orc.icp_extended(scan, map_pts, 6, -1.0, nn="brute", solver="closed")       # lowest index on ties
+    assert (o.indices[-1] < 9000).any()                                             # ties are exercised
+    for n_shards in (1, 2):
+        shards = []
+        for g in range(n_shards):
+            lo, hi = b200.shard_range(len(map_pts), g, n_shards)
+            shards.append(b200.MapShard(torch.from_numpy(map_pts[lo:hi]).cuda(), global_offset=lo,
+                                        spatial_sort=False))                        # scanned as given
+        run = b200.scan_to_map.ScanToMapLocalShards(shards, len(scan))
+        run.init(torch.from_numpy(scan).cuda())
+        for it in range(6):
+            run.step(6, -1.0)
+            idx = run.indices.cpu().numpy()
+            assert np.array_equal(idx, o.indices[it]), (n_shards, it, int(np.sum(idx != o.indices[it])))
+            assert idx.max() < 24000                                                # never the later copy
