@@ -838,10 +838,15 @@ __global__ void __launch_bounds__(kUpdateThreads) s2m_update_kernel(const Update
   __syncthreads();
   if (ticket != gridDim.x - 1) return;
   // ---- last CTA: add the partials by CTA index (fixed order), solve, decide
+  // (all partials are fetched at once by the whole CTA -- one memory round trip instead of one per
+  // CTA -- and then added in CTA order from shared memory: the same additions, the same bits)
   __threadfence();
+  __shared__ double part[kMaxUpdateCtas * 12];
+  for (unsigned q = tid; q < gridDim.x * 12u; q += kUpdateThreads) part[q] = __ldcg(partials + q);
+  __syncthreads();
   if (tid < 11) {
     double acc = 0.0;
-    for (unsigned c = 0; c < gridDim.x; ++c) acc += __ldcg(partials + c * 12 + tid);
+    for (unsigned c = 0; c < gridDim.x; ++c) acc += part[c * 12 + tid];
     tot[tid] = acc;
   }
   __syncthreads();

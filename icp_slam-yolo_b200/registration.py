@@ -381,16 +381,30 @@ class HostPipeline:
     makes.  Pinned host tables are streamed to the device in chunks (sizes: ``chunk_schedule``) on a
     copy stream while the previous chunk's ICP kernel runs, and each chunk's poses / errors / iteration counts
     are copied back to pinned host memory, so host<->device traffic overlaps the compute.
-    Consecutive chunks run on two alternating compute streams: the next chunk's CTAs fill the SMs
-    that the tail wave of the current chunk leaves idle.
+    Consecutive chunks run on alternating compute streams (one per staging buffer, three by default):
+    the next chunk's CTAs fill the SMs that the tail wave of the current chunk leaves idle.
 
     Device staging buffers and pinned result buffers are allocated once and reused.
+
+    ``graph=True``: a run (~16 chunks, ~100 enqueue calls from Python) is captured once per (host
+    buffers, arguments) as a CUDA graph -- on the second call with the same pinned tensors, after an
+    eager first call -- and replayed afterwards: one launch per run, the same kernels, copies and
+    dependencies, the same bits.  Off by default: on the benchmark the host keeps ahead of the GPU
+    either way (9.087 vs 9.088 ms per run); it pays when the host thread is busy with other work.
     """
 
     def __init__(self, n_pairs: int, src_pitch: int, tgt_pitch: int, dtype=torch.float32,
-                 chunks: int = 8, device="cuda"):
+                 chunks: int = 8, device="cuda", graph: bool = False, buffers: int = 3):
         self.n_pairs, self.src_pitch, self.tgt_pitch = int(n_pairs), int(src_pitch), int(tgt_pitch)
         self.device = torch.device(device)
+        self.use_graph = bool(graph)
+        # Staging buffers = compute streams.  The copy of chunk i may start once the kernel of chunk
+        # i - buffers has ended.  With two buffers it ends only ~0.25 ms before the kernel of chunk i - 1
+        # does (copy 0.86 ms, kernel 1.11 ms per 8,192 pairs), which is the length of that kernel's
+        # tail wave: the next kernel arrived too late to fill it, and a run cost the sum of the
+        # ISOLATED chunk times (9.8 ms) instead of the work (8.9 ms).  Three buffers give the slack.
+        self.nbuf = max(2, int(buffers))
+        self._graphs, self._seen, self._graph_launches = {}, set(), 0
         sizes = self.chunk_schedule(self.n_pairs, chunks)
         self.chunk = max(sizes)
         self.bounds = [0]
@@ -401,10 +415,10 @@ class HostPipeline:
         mk = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, device=self.device)
         self.bufs = [dict(src=mk(c, src_pitch, 2), tgt=mk(c, tgt_pitch, 2),
                           slen=mk(c, dt=torch.int32), tlen=mk(c, dt=torch.int32),
-                          out=alloc_outputs(c, src_pitch, self.device)) for _ in range(2)]
+                          out=alloc_outputs(c, src_pitch, self.device)) for _ in range(self.nbuf)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.out_stream = torch.cuda.Stream(device=self.device)
-        self.compute_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self.compute_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.nbuf)]
         # one fused kernel for every chunk, chosen on the size of the whole batch: results must not
         # depend on how the batch is cut (the two kernels agree to ~1e-12, not bit for bit)
         self.kernel = "warp" if self.n_pairs > 512 else "cta"
@@ -422,10 +436,9 @@ class HostPipeline:
         """Chunk sizes of one run.  ``chunks`` sets the LARGEST chunk (n_pairs / chunks).  Two parts of
         the pipeline cannot be hidden: the first host-to-device copy (nothing to compute yet) and the
         last kernel (nothing left to copy).  So the sizes ramp up geometrically from 1/8 of the largest
-        chunk -- with two staging buffers, copy i+1 starts when kernel i-1 has ended and must end before
-        kernel i does, which holds while the chunks grow by no more than the kernel / copy time ratio
-        (1.3 on the headline workload; a regular second chunk after a short first one left the GPU idle
-        for 0.7 ms of a 9.8 ms step) -- and the run ends with two shrinking chunks (1/2 and 1/4 of the
+        chunk -- a copy must end before the kernel ahead of it does, which holds while the chunks grow
+        by no more than the kernel / copy time ratio (1.3 on the headline workload) -- and the run ends
+        with shrinking chunks (1/2 and 1/4 of the
         largest), which is what a copy-bound run (several GPUs sharing the host's memory bandwidth)
         exposes after its last copy."""
         n_pairs, chunks = int(n_pairs), max(1, int(chunks))
@@ -475,22 +488,52 @@ class HostPipeline:
         if ragged:
             self._check_host(h_src_len, "h_src_len", (self.n_pairs,), torch.int32)
             self._check_host(h_tgt_len, "h_tgt_len", (self.n_pairs,), torch.int32)
+        key = (h_src.data_ptr(), h_tgt.data_ptr(), h_src_len.data_ptr() if ragged else 0,
+               h_tgt_len.data_ptr() if ragged else 0, int(max_iterations), float(tolerance),
+               None if max_corr_dist is None else float(max_corr_dist))
+        args = (h_src, h_tgt, h_src_len, h_tgt_len, ragged, max_iterations, tolerance, max_corr_dist)
+        g = self._graphs.get(key) if self.use_graph else None
+        if g is None and self.use_graph and key in self._seen:
+            # second run on these buffers: capture (the first one ran eagerly: lazy one-time set-up of
+            # the kernels is done).  The captured graph holds the tensors' addresses, not the tensors.
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.device(self.device), torch.cuda.graph(g):
+                self._enqueue(*args)
+            self._graphs[key] = g
+            self._graph_launches = self.launches
+        main = torch.cuda.current_stream(self.device)
+        if g is not None:
+            with torch.cuda.device(self.device):
+                g.replay()
+            self.launches = self._graph_launches
+        else:
+            self._seen.add(key)
+            self._enqueue(*args)
+        self.done_event = torch.cuda.Event()
+        self.done_event.record(main)
+        return self.h_pose, self.h_error, self.h_iters
+
+    def _enqueue(self, h_src, h_tgt, h_src_len, h_tgt_len, ragged, max_iterations, tolerance, max_corr_dist):
+        """One run's copies and kernels, enqueued on the side streams (forked from and joined back to the
+        current stream, so the whole of it can be captured in a CUDA graph)."""
         main = torch.cuda.current_stream(self.device)
         # the previous run() ended with `main` waiting for all of its copies and kernels; ordering
         # the side streams after `main` keeps this run's first copies out of staging buffers that
         # the previous run's kernels may still be reading
         self.copy_stream.wait_stream(main)
         self.out_stream.wait_stream(main)
-        ready = [None, None]       # compute-done events per staging buffer
-        drained = [None, None]     # results-copied events per staging buffer
+        nb_ = self.nbuf
+        ready = [None] * nb_       # compute-done events per staging buffer
+        drained = [None] * nb_     # results-copied events per staging buffer
         self.launches = 0
         for ci in range(len(self.bounds) - 1):
             b0, b1 = self.bounds[ci], self.bounds[ci + 1]
             nb = b1 - b0
-            buf = self.bufs[ci & 1]
+            bi = ci % nb_
+            buf = self.bufs[bi]
             with torch.cuda.stream(self.copy_stream):
-                if ready[ci & 1] is not None:
-                    self.copy_stream.wait_event(ready[ci & 1])      # kernel finished reading it
+                if ready[bi] is not None:
+                    self.copy_stream.wait_event(ready[bi])          # kernel finished reading it
                 buf["src"][:nb].copy_(h_src[b0:b1], non_blocking=True)
                 buf["tgt"][:nb].copy_(h_tgt[b0:b1], non_blocking=True)
                 if ragged:
@@ -498,12 +541,12 @@ class HostPipeline:
                     buf["tlen"][:nb].copy_(h_tgt_len[b0:b1], non_blocking=True)
                 copied = torch.cuda.Event()
                 copied.record(self.copy_stream)
-            cs = self.compute_streams[ci & 1]
-            if ci < 2:
+            cs = self.compute_streams[bi]
+            if ci < nb_:
                 cs.wait_stream(main)                                # work queued by the caller before run()
             cs.wait_event(copied)
-            if drained[ci & 1] is not None:
-                cs.wait_event(drained[ci & 1])                      # previous results left the buffer
+            if drained[bi] is not None:
+                cs.wait_event(drained[bi])                          # previous results left the buffer
             s = ScanTable(buf["src"][:nb], buf["slen"][:nb] if ragged else None)
             t = ScanTable(buf["tgt"][:nb], buf["tlen"][:nb] if ragged else None)
             with torch.cuda.stream(cs):
@@ -512,7 +555,7 @@ class HostPipeline:
             self.launches += 1
             done = torch.cuda.Event()
             done.record(cs)
-            ready[ci & 1] = done
+            ready[bi] = done
             with torch.cuda.stream(self.out_stream):
                 self.out_stream.wait_event(done)
                 self.h_pose[b0:b1].copy_(buf["out"].pose_total[:nb], non_blocking=True)
@@ -520,12 +563,11 @@ class HostPipeline:
                 self.h_iters[b0:b1].copy_(buf["out"].iterations[:nb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.out_stream)
-                drained[ci & 1] = ev
+                drained[bi] = ev
         for ev in drained:
             if ev is not None:
                 main.wait_event(ev)
         for cs in self.compute_streams:
             main.wait_stream(cs)
-        self.done_event = torch.cuda.Event()
-        self.done_event.record(main)
-        return self.h_pose, self.h_error, self.h_iters
+        main.wait_stream(self.copy_stream)
+        main.wait_stream(self.out_stream)

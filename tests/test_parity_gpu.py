@@ -499,7 +499,7 @@ def test_host_pipeline_back_to_back_runs_do_not_race(b200):
     s2, t2 = orc.synth_room_batch(50000, n)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     h = [pin(s1), pin(t1), pin(s2), pin(t2)]
-    pipe = b200.registration.HostPipeline(n, 360, 360, dtype=torch.float32, chunks=4)
+    pipe = b200.registration.HostPipeline(n, 360, 360, dtype=torch.float32, chunks=4, graph=True)
     for rep in range(3):
         pa, _, _ = pipe.run(h[0], h[1], max_iterations=30, tolerance=-1.0)
         if rep == 0:                                        # keep the first run's result once (needs a sync)
@@ -514,6 +514,15 @@ def test_host_pipeline_back_to_back_runs_do_not_race(b200):
     ref1 = b200.align_pairs(b200.ScanTable(h[0].cuda()), b200.ScanTable(h[1].cuda()), max_iterations=30,
                             tolerance=-1.0, kernel="warp")
     assert torch.equal(first, ref1.pose_total.cpu())
+    assert len(pipe._graphs) == 2             # repetitions 1 and 2 were CUDA-graph captures / replays of both runs
+    pa, _, _ = pipe.run(h[0], h[1], max_iterations=30, tolerance=-1.0)                  # a replay, checked on its own
+    pipe.done_event.synchronize()
+    assert torch.equal(pa, ref1.pose_total.cpu())
+    eager = b200.registration.HostPipeline(n, 360, 360, dtype=torch.float32, chunks=4, graph=False)
+    for _ in range(2):
+        pe, _, _ = eager.run(h[0], h[1], max_iterations=30, tolerance=-1.0)
+    eager.done_event.synchronize()
+    assert torch.equal(pe, ref1.pose_total.cpu()) and not eager._graphs
     with pytest.raises(ValueError):
         pipe.run(h[0], h[1], torch.zeros(n, dtype=torch.int32).pin_memory(), None)      # one length array only
     with pytest.raises(ValueError):
