@@ -6,7 +6,7 @@ labels_segmentation/icp.py:28-53.  The map is split into contiguous index ranges
 rank.  Once per map the bounding circles of every 1,024-point chunk of every rank are gathered
 (32 bytes per chunk), so each rank can bound a scan point's nearest-neighbour distance over the
 whole map on its own.  Per iteration two kernels run on every rank: the search finds the exact
-nearest point of ITS shard for every scan point that can have its neighbour there (float64 scan
+nearest point of ITS shard for every scan point that can have its neighbour there (exact scan
 of the few chunks within the bound) and stores the 32-byte record straight into every rank's
 inbox over NVLink; the update waits for all ranks' flags, picks the global winner per point and
 solves the pose -- on the same records everywhere, so poses, errors and the stop decision are

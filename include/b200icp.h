@@ -39,7 +39,7 @@ extern "C" {
 
 #define B200ICP_VERSION_MAJOR 0
 #define B200ICP_VERSION_MINOR 3   /* 0.3: W-warps-per-pair fused kernel; scan-to-map = exact culling +
-                                     float64 scan with the all-gather in the search epilogue */
+                                     exact scan with the all-gather in the search epilogue */
 
 typedef enum b200icp_status {
   B200ICP_OK = 0,
@@ -213,7 +213,8 @@ int b200icp_polar_to_cartesian(const double* raw, const int32_t* raw_len, int32_
  *     b200icp_s2m_search  applies the pose increment the previous update left pending; per scan
  *                         point an upper bound of its NN distance (distance to the previous
  *                         iteration's nearest map point; circles in the first iteration); exhaustive
- *                         float64 scan of every local chunk whose circle is within that bound ->
+ *                         exact scan (float64 decisions; an FP32 test only skips points proven
+ *                         farther than the bound) of every local chunk whose circle is within it ->
  *                         the exact nearest point of THIS shard among all that can matter (lowest
  *                         index on ties) or "none"; the 32-byte record goes to `records`, or, with
  *                         `peers`, straight into every rank's inbox over NVLink, followed by this
