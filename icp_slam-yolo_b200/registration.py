@@ -507,7 +507,10 @@ class HostPipeline:
                 g.replay()
             self.launches = self._graph_launches
         else:
-            self._seen.add(key)
+            if self.use_graph:
+                if len(self._seen) > 64:              # callers that never reuse their buffers: stop tracking
+                    self._seen.clear()
+                self._seen.add(key)
             self._enqueue(*args)
         self.done_event = torch.cuda.Event()
         self.done_event.record(main)
